@@ -1,0 +1,18 @@
+"""B200-native per-object, per-channel hand-crafted feature extraction.
+
+Drop-in for the extraction step of
+aliechoes/interpretable-multichannel-image-analysis' ``channel_importance_hand_crafted_features``
+notebook (cell 13 functions + the cell 17 loop).  All arithmetic runs in hand-written sm_100a CUDA
+kernels behind the C ABI of ``include/imfeat.h``; there is no CPU fallback.
+"""
+from . import ablation, distributed, schema, synth
+from ._lib import ImfeatError
+from .extractor import (FeatureExtractor, basic_statistical_features, extract_features,
+                        get_extractor, glcm_features, plane_stride_for)
+from .schema import feature_columns
+
+__all__ = [
+    "FeatureExtractor", "ImfeatError", "basic_statistical_features", "extract_features",
+    "feature_columns", "get_extractor", "glcm_features", "plane_stride_for", "schema",
+    "ablation", "distributed", "synth",
+]

@@ -1,0 +1,92 @@
+// common.cuh -- shared device helpers for the feature kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace imfeat {
+
+constexpr int kNBasic = 17;
+constexpr int kNGlcm = 6;
+constexpr int kNShape = 10;
+constexpr int kNMoment = 9;
+constexpr int kMaxAngles = 4;
+constexpr int kMaxPixels = 32768;
+constexpr int kLevels = 256;
+
+constexpr uint32_t kStEmptyMask = 1u;
+constexpr uint32_t kStNoPairs = 2u;
+constexpr uint32_t kStConstant = 4u;
+
+// Everything a kernel needs to find its tiles and its output columns.  A "tile" is one
+// (output row, channel slot) plane: tile t -> row t / c_out, slot t % c_out.
+struct Params {
+    const uint16_t* planes;
+    const uint8_t* masks;      // nullable
+    const int32_t* sizes;      // nullable, [N][2]
+    const int32_t* src_obj;    // nullable, [N][c_out]
+    const int32_t* chan;       // nullable, [c_out]
+    double* out;
+    uint32_t* status;          // nullable
+    const double* log2tab;     // log2(k), k = 0..kMaxPixels (k=0 -> 0)
+    uint32_t* counts;          // nullable: GLCM bin dump [tile][angle][65536]
+    long long n_tiles;
+    long long plane_stride;
+    long long row_stride;
+    int c_in, c_out, hs, ws;
+    int col_basic, col_glcm, col_shape, col_moment;  // block bases (col_* < 0: block absent)
+    int n_angles;
+    int dr[kMaxAngles], dc[kMaxAngles];
+    double quant[9];           // percentile q / 100, computed on the host like numpy does
+};
+
+struct Tile {
+    const uint16_t* px;
+    const uint8_t* mk;
+    double* out_row;
+    uint32_t* status;
+    int slot, h, w, n;
+};
+
+__device__ __forceinline__ Tile resolve_tile(const Params& P, long long t) {
+    Tile T;
+    const long long row = t / P.c_out;
+    const int slot = (int)(t - row * P.c_out);
+    const long long so = P.src_obj ? (long long)P.src_obj[t] : row;
+    const int ch = P.chan ? P.chan[slot] : slot;
+    T.h = P.sizes ? P.sizes[2 * so] : P.hs;
+    T.w = P.sizes ? P.sizes[2 * so + 1] : P.ws;
+    T.n = T.h * T.w;
+    const long long off = (so * P.c_in + ch) * P.plane_stride;
+    T.px = P.planes + off;
+    T.mk = P.masks ? P.masks + off : nullptr;
+    T.out_row = P.out + row * P.row_stride;
+    T.status = P.status ? P.status + row : nullptr;
+    T.slot = slot;
+    return T;
+}
+
+// 128-bit streaming load: the tile is read once per kernel, keep it out of L1.
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+// 128-bit load that may be re-read by the same SM a few microseconds later (allocate in L1).
+__device__ __forceinline__ uint4 ld_reuse(const uint4* p) { return __ldg(p); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+}  // namespace imfeat

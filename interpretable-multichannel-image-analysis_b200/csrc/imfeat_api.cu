@@ -1,0 +1,548 @@
+// imfeat_api.cu -- the C ABI declared in include/imfeat.h (single translation unit, sm_100a).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/imfeat.h"
+#include "aux_kernels.cuh"
+#include "common.cuh"
+#include "k1_moments.cuh"
+#include "k2_order_entropy.cuh"
+#include "k3_glcm.cuh"
+#include "k4_shape.cuh"
+
+using namespace imfeat;
+
+static_assert(kNBasic == IMFEAT_N_BASIC && kNGlcm == IMFEAT_N_GLCM, "header mismatch");
+static_assert(kNShape == IMFEAT_N_SHAPE && kNMoment == IMFEAT_N_MOMENT, "header mismatch");
+static_assert(kMaxPixels == IMFEAT_MAX_PIXELS && kMaxAngles == IMFEAT_MAX_ANGLES, "header mismatch");
+
+constexpr int kTimingSlots = 64;
+
+struct imfeat_ctx {
+    int device;
+    int sm_count;
+    double* d_log2tab;
+    long long launches;
+    char err[512];
+    // host-path staging (lazily sized)
+    cudaStream_t streams[2];
+    cudaEvent_t done[2];
+    void* pin_in[2];
+    void* pin_out[2];
+    void* dev_in[2];
+    void* dev_out[2];
+    size_t in_bytes, out_bytes;
+    // optional per-kernel timing (imfeat_enable_timing): a ring of event sets, resolved lazily
+    int timing;
+    int t_head, t_pending;
+    cudaEvent_t t_ev[kTimingSlots][5];
+    unsigned t_mask[kTimingSlots];
+    double t_ms[4];
+    long long t_calls[4];
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(imfeat_ctx* ctx, int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    if (ctx) memcpy(ctx->err, g_err, sizeof(g_err));
+    return code;
+}
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(ctx, IMFEAT_ERR_CUDA, "%s failed: %s (%s:%d)", #call,             \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                      \
+    } while (0)
+
+extern "C" {
+
+void imfeat_default_opts(imfeat_opts* o) {
+    memset(o, 0, sizeof(*o));
+    o->struct_size = (int32_t)sizeof(*o);
+    o->want_basic = 1;
+    o->want_glcm = 1;
+    o->n_angles = 1;
+    o->glcm_distance = 5;
+    for (int k = 0; k < 9; ++k) o->percentiles[k] = (double)(k + 1) / 10.0;
+}
+
+int imfeat_abi_version(void) { return IMFEAT_ABI_VERSION; }
+
+const char* imfeat_last_error(const imfeat_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+int64_t imfeat_launch_count(const imfeat_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int64_t imfeat_row_width(int32_t c_out, const imfeat_opts* o) {
+    if (!o || c_out < 0) return -1;
+    int64_t per = 0;
+    if (o->want_basic) per += kNBasic;
+    if (o->want_glcm) per += kNGlcm * o->n_angles;
+    if (o->want_shape) per += kNShape;
+    if (o->want_moments) per += kNMoment;
+    return per * c_out;
+}
+
+int imfeat_create(int device, imfeat_ctx** out_ctx) {
+    imfeat_ctx* ctx = nullptr;
+    if (!out_ctx) return fail(nullptr, IMFEAT_ERR_ARG, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count)
+        return fail(nullptr, IMFEAT_ERR_ARG, "device %d out of range (%d CUDA devices)", device, count);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, IMFEAT_ERR_ARG,
+                    "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    ctx = (imfeat_ctx*)calloc(1, sizeof(imfeat_ctx));
+    if (!ctx) return fail(nullptr, IMFEAT_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    // log2 table, computed on the host in double precision (k = 0 maps to 0, never used)
+    double* tab = (double*)malloc(sizeof(double) * (kMaxPixels + 1));
+    if (!tab) { free(ctx); return fail(nullptr, IMFEAT_ERR_NOMEM, "out of host memory"); }
+    tab[0] = 0.0;
+    for (int k = 1; k <= kMaxPixels; ++k) tab[k] = log2((double)k);
+    cudaError_t e = cudaMalloc(&ctx->d_log2tab, sizeof(double) * (kMaxPixels + 1));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(ctx->d_log2tab, tab, sizeof(double) * (kMaxPixels + 1), cudaMemcpyHostToDevice);
+    free(tab);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_order_entropy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_order_entropy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k4_shape_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k4_shape_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
+    if (e != cudaSuccess) {
+        int rc = fail(nullptr, IMFEAT_ERR_CUDA, "context set-up failed: %s", cudaGetErrorString(e));
+        if (ctx->d_log2tab) cudaFree(ctx->d_log2tab);
+        free(ctx);
+        return rc;
+    }
+    *out_ctx = ctx;
+    return IMFEAT_OK;
+}
+
+static void free_staging(imfeat_ctx* ctx) {
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->pin_in[b]) cudaFreeHost(ctx->pin_in[b]);
+        if (ctx->pin_out[b]) cudaFreeHost(ctx->pin_out[b]);
+        if (ctx->dev_in[b]) cudaFree(ctx->dev_in[b]);
+        if (ctx->dev_out[b]) cudaFree(ctx->dev_out[b]);
+        ctx->pin_in[b] = ctx->pin_out[b] = ctx->dev_in[b] = ctx->dev_out[b] = nullptr;
+    }
+    ctx->in_bytes = ctx->out_bytes = 0;
+}
+
+int imfeat_destroy(imfeat_ctx* ctx) {
+    if (!ctx) return IMFEAT_OK;
+    cudaSetDevice(ctx->device);
+    free_staging(ctx);
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->streams[b]) cudaStreamDestroy(ctx->streams[b]);
+        if (ctx->done[b]) cudaEventDestroy(ctx->done[b]);
+    }
+    for (int sl = 0; sl < kTimingSlots; ++sl)
+        for (int k = 0; k < 5; ++k)
+            if (ctx->t_ev[sl][k]) cudaEventDestroy(ctx->t_ev[sl][k]);
+    if (ctx->d_log2tab) cudaFree(ctx->d_log2tab);
+    free(ctx);
+    return IMFEAT_OK;
+}
+
+}  // extern "C"
+
+// C round(): half away from zero, as skimage's _glcm_loop uses for the pixel offsets.
+static int c_round(double v) { return (int)(v < 0 ? -floor(-v + 0.5) : floor(v + 0.5)); }
+
+static int check_common(imfeat_ctx* ctx, const void* planes, int64_t n, int c_in, int c_out, int hs,
+                        int ws, int64_t plane_stride, const imfeat_opts* o) {
+    if (!ctx) return fail(nullptr, IMFEAT_ERR_ARG, "ctx is NULL");
+    if (!o || o->struct_size != (int32_t)sizeof(imfeat_opts))
+        return fail(ctx, IMFEAT_ERR_ARG, "opts is NULL or has the wrong struct_size");
+    if (n < 0) return fail(ctx, IMFEAT_ERR_ARG, "n_objects < 0");
+    if (n > 0 && !planes) return fail(ctx, IMFEAT_ERR_ARG, "planes is NULL");
+    if (c_in < 1 || c_out < 1) return fail(ctx, IMFEAT_ERR_ARG, "channel counts must be >= 1");
+    if (hs < 1 || ws < 1 || (int64_t)hs * ws > kMaxPixels)
+        return fail(ctx, IMFEAT_ERR_ARG, "object size %dx%d outside 1..%d pixels per plane", hs, ws, kMaxPixels);
+    if (plane_stride < (int64_t)hs * ws || (plane_stride & 7))
+        return fail(ctx, IMFEAT_ERR_ARG, "plane_stride must be >= hs*ws and a multiple of 8");
+    if (((uintptr_t)planes & 15) != 0) return fail(ctx, IMFEAT_ERR_ARG, "planes must be 16-byte aligned");
+    if (o->want_glcm && (o->n_angles < 1 || o->n_angles > kMaxAngles))
+        return fail(ctx, IMFEAT_ERR_ARG, "n_angles must be 1..%d", kMaxAngles);
+    if (o->want_glcm && (o->glcm_distance < 1 || o->glcm_distance > 255))
+        return fail(ctx, IMFEAT_ERR_ARG, "glcm_distance must be 1..255");
+    for (int k = 0; k < 9; ++k)
+        if (!(o->percentiles[k] >= 0.0 && o->percentiles[k] <= 100.0))
+            return fail(ctx, IMFEAT_ERR_ARG, "percentiles must lie in [0, 100]");
+    return IMFEAT_OK;
+}
+
+static void fill_params(Params& P, imfeat_ctx* ctx, const uint16_t* planes, const uint8_t* masks,
+                        const int32_t* sizes, const int32_t* src_obj, const int32_t* chan, int64_t n,
+                        int c_in, int c_out, int hs, int ws, int64_t plane_stride,
+                        const imfeat_opts* o, double* out, int64_t row_stride, uint32_t* status) {
+    memset(&P, 0, sizeof(P));
+    P.planes = planes; P.masks = masks; P.sizes = sizes; P.src_obj = src_obj; P.chan = chan;
+    P.out = out; P.status = status; P.log2tab = ctx->d_log2tab; P.counts = nullptr;
+    P.n_tiles = n * c_out; P.plane_stride = plane_stride; P.row_stride = row_stride;
+    P.c_in = c_in; P.c_out = c_out; P.hs = hs; P.ws = ws;
+    int col = 0;
+    P.col_basic = o->want_basic ? col : -1;   col += o->want_basic ? kNBasic * c_out : 0;
+    P.col_glcm = o->want_glcm ? col : -1;     col += o->want_glcm ? kNGlcm * o->n_angles * c_out : 0;
+    P.col_shape = o->want_shape ? col : -1;   col += o->want_shape ? kNShape * c_out : 0;
+    P.col_moment = o->want_moments ? col : -1;
+    P.n_angles = o->want_glcm ? o->n_angles : 0;
+    const double PI = 3.14159265358979323846;
+    const double ang[4] = {0.0, PI / 4, PI / 2, 3 * PI / 4};
+    for (int a = 0; a < kMaxAngles; ++a) {
+        P.dr[a] = c_round(sin(ang[a]) * o->glcm_distance);
+        P.dc[a] = c_round(cos(ang[a]) * o->glcm_distance);
+    }
+    for (int k = 0; k < 9; ++k) P.quant[k] = o->percentiles[k] / 100.0;   // numpy: true_divide(q, 100)
+}
+
+// Timing ring: slot = {ev[0..4]} recorded around K1,K2,K3,K4 of one extract call; mask bit k set
+// when kernel k ran.  Slots are resolved (synchronised + accumulated) lazily, so enabling timing
+// does not serialise the stream.
+static int timing_resolve(imfeat_ctx* ctx, int slot) {
+    const unsigned m = ctx->t_mask[slot];
+    if (!m) return IMFEAT_OK;
+    int last = 0;
+    for (int k = 0; k < 4; ++k) if (m & (1u << k)) last = k + 1;
+    CU(cudaEventSynchronize(ctx->t_ev[slot][last]));
+    int prev = -1;
+    for (int k = 0; k < 4; ++k) {
+        if (!(m & (1u << k))) continue;
+        // the start event of kernel k is the most recent event recorded before it
+        int start = (prev < 0) ? 0 : prev + 1;
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ctx->t_ev[slot][start], ctx->t_ev[slot][k + 1]));
+        ctx->t_ms[k] += ms;
+        ctx->t_calls[k] += 1;
+        prev = k;
+    }
+    ctx->t_mask[slot] = 0;
+    return IMFEAT_OK;
+}
+
+static int launch_all(imfeat_ctx* ctx, const Params& P, const imfeat_opts* o, cudaStream_t st) {
+    if (P.n_tiles == 0) return IMFEAT_OK;
+    int slot = -1;
+    if (ctx->timing) {
+        slot = ctx->t_head;
+        ctx->t_head = (ctx->t_head + 1) % kTimingSlots;
+        int rc = timing_resolve(ctx, slot);
+        if (rc) return rc;
+        for (int k = 0; k < 5; ++k)
+            if (!ctx->t_ev[slot][k]) CU(cudaEventCreate(&ctx->t_ev[slot][k]));
+        CU(cudaEventRecord(ctx->t_ev[slot][0], st));
+    }
+#define IMFEAT_MARK(k)                                                  \
+    if (slot >= 0) {                                                    \
+        CU(cudaEventRecord(ctx->t_ev[slot][(k) + 1], st));              \
+        ctx->t_mask[slot] |= 1u << (k);                                 \
+    }
+    const bool masked = P.masks != nullptr;
+    const long long sm = ctx->sm_count;
+    if (o->want_basic) {
+        const int g1 = (int)((P.n_tiles + 7) / 8 < sm * 8 ? (P.n_tiles + 7) / 8 : sm * 8);
+        if (masked) k1_moments_kernel<true><<<g1, 256, 0, st>>>(P);
+        else k1_moments_kernel<false><<<g1, 256, 0, st>>>(P);
+        IMFEAT_MARK(0)
+        const int g2 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
+        if (masked) k2_order_entropy_kernel<true><<<g2, kK2Threads, sizeof(K2Smem), st>>>(P);
+        else k2_order_entropy_kernel<false><<<g2, kK2Threads, sizeof(K2Smem), st>>>(P);
+        IMFEAT_MARK(1)
+        ctx->launches += 2;
+    }
+    if (o->want_glcm) {
+        const int g3 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
+        if (masked) k3_glcm_kernel<true, false><<<g3, kK3Threads, sizeof(K3Smem), st>>>(P);
+        else k3_glcm_kernel<false, false><<<g3, kK3Threads, sizeof(K3Smem), st>>>(P);
+        IMFEAT_MARK(2)
+        ctx->launches += 1;
+    }
+    if (o->want_shape || o->want_moments) {
+        const int g4 = (int)(P.n_tiles < sm * 3 ? P.n_tiles : sm * 3);
+        if (masked) k4_shape_kernel<true><<<g4, kK4Threads, sizeof(K4Smem), st>>>(P);
+        else k4_shape_kernel<false><<<g4, kK4Threads, sizeof(K4Smem), st>>>(P);
+        IMFEAT_MARK(3)
+        ctx->launches += 1;
+    }
+#undef IMFEAT_MARK
+    CU(cudaGetLastError());
+    return IMFEAT_OK;
+}
+
+extern "C" {
+
+int imfeat_enable_timing(imfeat_ctx* ctx, int32_t enable) {
+    if (!ctx) return fail(nullptr, IMFEAT_ERR_ARG, "ctx is NULL");
+    ctx->timing = enable ? 1 : 0;
+    return IMFEAT_OK;
+}
+
+int imfeat_kernel_times(imfeat_ctx* ctx, double* ms_out, int64_t* calls_out, int32_t reset) {
+    if (!ctx) return fail(nullptr, IMFEAT_ERR_ARG, "ctx is NULL");
+    CU(cudaSetDevice(ctx->device));
+    for (int sl = 0; sl < kTimingSlots; ++sl) {
+        int rc = timing_resolve(ctx, sl);
+        if (rc) return rc;
+    }
+    for (int k = 0; k < 4; ++k) {
+        if (ms_out) ms_out[k] = ctx->t_ms[k];
+        if (calls_out) calls_out[k] = ctx->t_calls[k];
+        if (reset) { ctx->t_ms[k] = 0.0; ctx->t_calls[k] = 0; }
+    }
+    return IMFEAT_OK;
+}
+
+int imfeat_extract_device(imfeat_ctx* ctx, const uint16_t* d_planes, const uint8_t* d_masks,
+                          const int32_t* d_sizes, const int32_t* d_src_obj, const int32_t* d_chan,
+                          int64_t n_objects, int32_t c_in, int32_t c_out, int32_t hs, int32_t ws,
+                          int64_t plane_stride, const imfeat_opts* opts, double* d_out,
+                          int64_t row_stride, uint32_t* d_status, void* stream) {
+    int rc = check_common(ctx, d_planes, n_objects, c_in, c_out, hs, ws, plane_stride, opts);
+    if (rc) return rc;
+    if (!d_chan && c_out != c_in)
+        return fail(ctx, IMFEAT_ERR_ARG, "c_out (%d) != c_in (%d) needs a channel list", c_out, c_in);
+    if (n_objects > 0 && !d_out) return fail(ctx, IMFEAT_ERR_ARG, "d_out is NULL");
+    if (row_stride < imfeat_row_width(c_out, opts))
+        return fail(ctx, IMFEAT_ERR_ARG, "row_stride %lld < row width %lld", (long long)row_stride,
+                    (long long)imfeat_row_width(c_out, opts));
+    if (d_masks && ((uintptr_t)d_masks & 7)) return fail(ctx, IMFEAT_ERR_ARG, "masks must be 8-byte aligned");
+    if (n_objects == 0) return IMFEAT_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_status) { CU(cudaMemsetAsync(d_status, 0, sizeof(uint32_t) * n_objects, st)); }
+    Params P;
+    fill_params(P, ctx, d_planes, d_masks, d_sizes, d_src_obj, d_chan, n_objects, c_in, c_out, hs,
+                ws, plane_stride, opts, d_out, row_stride, d_status);
+    return launch_all(ctx, P, opts, st);
+}
+
+int imfeat_glcm_counts_device(imfeat_ctx* ctx, const uint16_t* d_planes, const uint8_t* d_masks,
+                              const int32_t* d_sizes, int64_t n_objects, int32_t c, int32_t hs,
+                              int32_t ws, int64_t plane_stride, const imfeat_opts* opts,
+                              uint32_t* d_counts, void* stream) {
+    int rc = check_common(ctx, d_planes, n_objects, c, c, hs, ws, plane_stride, opts);
+    if (rc) return rc;
+    if (!opts->want_glcm) return fail(ctx, IMFEAT_ERR_ARG, "opts->want_glcm must be set");
+    if (n_objects > 0 && !d_counts) return fail(ctx, IMFEAT_ERR_ARG, "d_counts is NULL");
+    if (n_objects == 0) return IMFEAT_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // the property columns are computed too; park them in a scratch table
+    imfeat_opts o = *opts;
+    o.want_basic = 0; o.want_shape = 0; o.want_moments = 0;
+    const int64_t width = imfeat_row_width(c, &o);
+    double* scratch = nullptr;
+    CU(cudaMallocAsync((void**)&scratch, sizeof(double) * width * n_objects, st));
+    Params P;
+    fill_params(P, ctx, d_planes, d_masks, d_sizes, nullptr, nullptr, n_objects, c, c, hs, ws,
+                plane_stride, &o, scratch, width, nullptr);
+    P.counts = d_counts;
+    const int g3 = (int)(P.n_tiles < ctx->sm_count ? P.n_tiles : ctx->sm_count);
+    if (d_masks) k3_glcm_kernel<true, true><<<g3, kK3Threads, sizeof(K3Smem), st>>>(P);
+    else k3_glcm_kernel<false, true><<<g3, kK3Threads, sizeof(K3Smem), st>>>(P);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(scratch, st));
+    return IMFEAT_OK;
+}
+
+int imfeat_pack_hwc_device(imfeat_ctx* ctx, const uint16_t* d_hwc, const uint8_t* d_mask_hwc,
+                           const int32_t* d_sizes, int64_t n_objects, int32_t c, int32_t hs,
+                           int32_t ws, int64_t plane_stride, uint16_t* d_planes, uint8_t* d_masks,
+                           void* stream) {
+    if (!ctx) return fail(nullptr, IMFEAT_ERR_ARG, "ctx is NULL");
+    if (n_objects < 0 || c < 1 || hs < 1 || ws < 1 || plane_stride < (int64_t)hs * ws)
+        return fail(ctx, IMFEAT_ERR_ARG, "bad shape");
+    if (n_objects == 0) return IMFEAT_OK;
+    if (!d_hwc || !d_planes) return fail(ctx, IMFEAT_ERR_ARG, "NULL image pointer");
+    if ((d_mask_hwc == nullptr) != (d_masks == nullptr))
+        return fail(ctx, IMFEAT_ERR_ARG, "mask input and output must both be given or both be NULL");
+    CU(cudaSetDevice(ctx->device));
+    const long long total = (long long)n_objects * hs * ws;
+    const long long want = (total + 255) / 256;
+    const int grid = (int)(want < (long long)ctx->sm_count * 16 ? want : (long long)ctx->sm_count * 16);
+    pack_hwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_hwc, d_mask_hwc, d_sizes, n_objects, c, hs,
+                                                           ws, plane_stride, d_planes, d_masks);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return IMFEAT_OK;
+}
+
+int imfeat_synth_device(imfeat_ctx* ctx, uint64_t seed, int64_t first_object, int64_t n_objects,
+                        int32_t c, int32_t hs, int32_t ws, int64_t plane_stride, int32_t variable,
+                        int32_t hmin, int32_t wmin, int32_t mask_shrink_256, uint16_t* d_planes,
+                        uint8_t* d_masks, int32_t* d_sizes, void* stream) {
+    if (!ctx) return fail(nullptr, IMFEAT_ERR_ARG, "ctx is NULL");
+    if (n_objects < 0 || c < 1 || hs < 1 || ws < 1 || plane_stride < (int64_t)hs * ws)
+        return fail(ctx, IMFEAT_ERR_ARG, "bad shape");
+    if (variable && (hmin < 1 || hmin > hs || wmin < 1 || wmin > ws || !d_sizes))
+        return fail(ctx, IMFEAT_ERR_ARG, "variable sizes need 1 <= hmin <= hs, 1 <= wmin <= ws and d_sizes");
+    if (n_objects == 0) return IMFEAT_OK;
+    if (!d_planes) return fail(ctx, IMFEAT_ERR_ARG, "d_planes is NULL");
+    CU(cudaSetDevice(ctx->device));
+    const long long planes = (long long)n_objects * c;
+    const int grid = (int)(planes < (long long)ctx->sm_count * 32 ? planes : (long long)ctx->sm_count * 32);
+    synth_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, first_object, n_objects, c, hs, ws,
+                                                        plane_stride, variable, hmin, wmin,
+                                                        mask_shrink_256, d_planes, d_masks, d_sizes);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return IMFEAT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer entry point: slab pipeline  (pinned staging -> H2D -> kernels -> D2H), two slabs in
+// flight on two streams so copies overlap the kernels of the neighbouring slab.
+// ---------------------------------------------------------------------------------------------
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// layout: 0 = plane-compact planar uint16[N][c][plane_stride]; 1 = interleaved README.md:8 layout
+// uint16[N][hs][ws][c] (valid region = top-left h_i x w_i), packed to planar on the device.
+static int extract_host_impl(imfeat_ctx* ctx, int layout, const uint16_t* h_img, const uint8_t* h_masks,
+                             const int32_t* h_sizes, int64_t n_objects, int32_t c, int32_t hs,
+                             int32_t ws, int64_t plane_stride, const imfeat_opts* opts, double* h_out,
+                             int64_t row_stride, uint32_t* h_status) {
+    int rc = check_common(ctx, h_img, n_objects, c, c, hs, ws, plane_stride, opts);
+    if (rc) return rc;
+    if (n_objects > 0 && !h_out) return fail(ctx, IMFEAT_ERR_ARG, "h_out is NULL");
+    const int64_t width = imfeat_row_width(c, opts);
+    if (row_stride < width) return fail(ctx, IMFEAT_ERR_ARG, "row_stride < row width");
+    if (n_objects == 0) return IMFEAT_OK;
+    CU(cudaSetDevice(ctx->device));
+    for (int b = 0; b < 2; ++b) {
+        if (!ctx->streams[b]) CU(cudaStreamCreateWithFlags(&ctx->streams[b], cudaStreamNonBlocking));
+        if (!ctx->done[b]) CU(cudaEventCreateWithFlags(&ctx->done[b], cudaEventDisableTiming));
+    }
+    const size_t src_px = layout ? (size_t)hs * ws * c : (size_t)c * plane_stride;  // host elems/object
+    const size_t pl_px = (size_t)c * plane_stride;                                  // planar elems/object
+    const size_t obj_in = src_px * 2 + (h_masks ? src_px : 0) + 8 +
+                          (layout ? pl_px * 2 + (h_masks ? pl_px : 0) : 0);
+    const size_t obj_out = (size_t)width * 8 + 4;
+    int64_t slab = (int64_t)(((size_t)64 << 20) / (src_px * 2));      // ~64 MiB of pixels per slab
+    if (slab < 1) slab = 1;
+    if (slab > n_objects) slab = n_objects;
+    const size_t need_in = (size_t)slab * obj_in + 256, need_out = (size_t)slab * obj_out + 64;
+    if (need_in > ctx->in_bytes || need_out > ctx->out_bytes) {
+        free_staging(ctx);
+        for (int b = 0; b < 2; ++b) {
+            CU(cudaMallocHost(&ctx->pin_in[b], need_in));
+            CU(cudaMallocHost(&ctx->pin_out[b], need_out));
+            CU(cudaMalloc(&ctx->dev_in[b], need_in));
+            CU(cudaMalloc(&ctx->dev_out[b], need_out));
+        }
+        ctx->in_bytes = need_in;
+        ctx->out_bytes = need_out;
+    }
+    const bool direct_in = is_pinned(h_img) && (!h_masks || is_pinned(h_masks));
+    const int64_t n_slabs = (n_objects + slab - 1) / slab;
+    // byte offsets inside a slab buffer: [pixels | masks | sizes | planar pixels | planar masks]
+    auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t off_mask = up16((size_t)slab * src_px * 2);
+    const size_t off_size = up16(off_mask + (h_masks ? (size_t)slab * src_px : 0));
+    const size_t off_plpx = up16(off_size + (size_t)slab * 8);
+    const size_t off_plmk = up16(off_plpx + (layout ? (size_t)slab * pl_px * 2 : 0));
+    const size_t off_stat = (size_t)slab * width * 8;
+    auto drain = [&](int64_t s) {   // copy slab s's results from pinned staging to the caller
+        const int b = (int)(s & 1);
+        const int64_t first = s * slab, cnt = (first + slab <= n_objects) ? slab : n_objects - first;
+        const double* src = (const double*)ctx->pin_out[b];
+        if (row_stride == width) memcpy(h_out + first * row_stride, src, (size_t)cnt * width * 8);
+        else for (int64_t i = 0; i < cnt; ++i) memcpy(h_out + (first + i) * row_stride, src + i * width, (size_t)width * 8);
+        if (h_status) memcpy(h_status + first, (const char*)ctx->pin_out[b] + off_stat, (size_t)cnt * 4);
+    };
+    for (int64_t s = 0; s < n_slabs; ++s) {
+        const int b = (int)(s & 1);
+        cudaStream_t st = ctx->streams[b];
+        const int64_t first = s * slab, cnt = (first + slab <= n_objects) ? slab : n_objects - first;
+        if (s >= 2) { CU(cudaEventSynchronize(ctx->done[b])); drain(s - 2); }
+        char* din = (char*)ctx->dev_in[b];
+        char* pin = (char*)ctx->pin_in[b];
+        const uint16_t* src_img = h_img + (size_t)first * src_px;
+        const uint8_t* src_mk = h_masks ? h_masks + (size_t)first * src_px : nullptr;
+        if (direct_in) {
+            CU(cudaMemcpyAsync(din, src_img, (size_t)cnt * src_px * 2, cudaMemcpyHostToDevice, st));
+            if (h_masks) CU(cudaMemcpyAsync(din + off_mask, src_mk, (size_t)cnt * src_px, cudaMemcpyHostToDevice, st));
+        } else {
+            memcpy(pin, src_img, (size_t)cnt * src_px * 2);
+            CU(cudaMemcpyAsync(din, pin, (size_t)cnt * src_px * 2, cudaMemcpyHostToDevice, st));
+            if (h_masks) {
+                memcpy(pin + off_mask, src_mk, (size_t)cnt * src_px);
+                CU(cudaMemcpyAsync(din + off_mask, pin + off_mask, (size_t)cnt * src_px, cudaMemcpyHostToDevice, st));
+            }
+        }
+        if (h_sizes) {
+            memcpy(pin + off_size, h_sizes + 2 * first, (size_t)cnt * 8);
+            CU(cudaMemcpyAsync(din + off_size, pin + off_size, (size_t)cnt * 8, cudaMemcpyHostToDevice, st));
+        }
+        const int32_t* d_sizes = h_sizes ? (const int32_t*)(din + off_size) : nullptr;
+        const uint16_t* d_planes = (const uint16_t*)din;
+        const uint8_t* d_masks = h_masks ? (const uint8_t*)(din + off_mask) : nullptr;
+        if (layout) {
+            rc = imfeat_pack_hwc_device(ctx, (const uint16_t*)din, d_masks, d_sizes, cnt, c, hs, ws, plane_stride,
+                                        (uint16_t*)(din + off_plpx), h_masks ? (uint8_t*)(din + off_plmk) : nullptr, st);
+            if (rc) return rc;
+            d_planes = (const uint16_t*)(din + off_plpx);
+            d_masks = h_masks ? (const uint8_t*)(din + off_plmk) : nullptr;
+        }
+        double* dout = (double*)ctx->dev_out[b];
+        uint32_t* dstat = (uint32_t*)((char*)ctx->dev_out[b] + off_stat);
+        CU(cudaMemsetAsync(dstat, 0, (size_t)cnt * 4, st));
+        Params P;
+        fill_params(P, ctx, d_planes, d_masks, d_sizes, nullptr, nullptr, cnt, c, c, hs, ws, plane_stride,
+                    opts, dout, width, dstat);
+        rc = launch_all(ctx, P, opts, st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(ctx->pin_out[b], dout, (size_t)cnt * width * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync((char*)ctx->pin_out[b] + off_stat, dstat, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(ctx->done[b], st));
+    }
+    for (int64_t s = (n_slabs >= 2 ? n_slabs - 2 : 0); s < n_slabs; ++s) {
+        CU(cudaEventSynchronize(ctx->done[s & 1]));
+        drain(s);
+    }
+    return IMFEAT_OK;
+}
+
+int imfeat_extract_host(imfeat_ctx* ctx, const uint16_t* h_planes, const uint8_t* h_masks,
+                        const int32_t* h_sizes, int64_t n_objects, int32_t c, int32_t hs, int32_t ws,
+                        int64_t plane_stride, const imfeat_opts* opts, double* h_out,
+                        int64_t row_stride, uint32_t* h_status) {
+    return extract_host_impl(ctx, 0, h_planes, h_masks, h_sizes, n_objects, c, hs, ws, plane_stride, opts,
+                             h_out, row_stride, h_status);
+}
+
+int imfeat_extract_host_hwc(imfeat_ctx* ctx, const uint16_t* h_hwc, const uint8_t* h_mask_hwc,
+                            const int32_t* h_sizes, int64_t n_objects, int32_t c, int32_t hs, int32_t ws,
+                            const imfeat_opts* opts, double* h_out, int64_t row_stride,
+                            uint32_t* h_status) {
+    const int64_t plane_stride = ((int64_t)hs * ws + 7) & ~(int64_t)7;
+    return extract_host_impl(ctx, 1, h_hwc, h_mask_hwc, h_sizes, n_objects, c, hs, ws, plane_stride, opts,
+                             h_out, row_stride, h_status);
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+INT_EXACT = ("min_intensity", "max_intensity", "total_intensity", "area", "bbox_area")
+BIT_EXACT = tuple("percentile%d0_intensity" % k for k in range(1, 10))
+
+
+def compare_tables(got, want, cols, rtol=1e-9, atol=1e-9, label=""):
+    """Integer-valued columns and percentiles must match bit for bit; floating columns within
+    rtol (north_star allows 1e-5; the kernels are held to 1e-9 here)."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert got.shape[1] == len(cols)
+    bad = []
+    for j, name in enumerate(cols):
+        g, w = got[:, j], want[:, j]
+        base = name.rsplit("_Ch", 1)[0]
+        if base in INT_EXACT or base in BIT_EXACT:
+            ok = (g == w) | (np.isnan(g) & np.isnan(w))
+        else:
+            ok = np.isclose(g, w, rtol=rtol, atol=atol, equal_nan=True)
+        if not ok.all():
+            i = int(np.flatnonzero(~ok)[0])
+            bad.append("%s row %d: got %r want %r" % (name, i, g[i], w[i]))
+    assert not bad, "%s %d bad columns, first: %s" % (label, len(bad), "; ".join(bad[:6]))
+
+
+@pytest.fixture(scope="session")
+def golden():
+    path = os.path.join(ROOT, "tests", "golden", "notebook_golden.npz")
+    z = np.load(path)
+    names = sorted(k[3:] for k in z.files if k.startswith("in_"))
+    return {n: (z["in_" + n], z["out_" + n], [str(c) for c in z["cols_" + n]]) for n in names}
+
+
+def parity_distributions(rng, h, w):
+    """The parity distributions of SURVEY.md 8(d), as a dict name -> uint16 [h, w]."""
+    yy, xx = np.mgrid[0:h, 0:w]
+    out = {
+        "uniform12": rng.integers(0, 4096, (h, w)),
+        "full16": rng.integers(0, 65536, (h, w)),
+        "ties8": rng.choice([3, 17, 17, 250, 900, 901, 4000, 65535], (h, w)),
+        "halfzero": np.clip(rng.normal(0, 300, (h, w)), 0, 65535),
+        "constant": np.full((h, w), 1234),
+        "allzero": np.zeros((h, w)),
+        "saturated": np.full((h, w), 65535),
+        "gradient": (yy * 37 + xx * 11) % 65536,
+        "poisson_blob": np.clip(rng.poisson(400, (h, w)) + 3000 * np.clip(
+            1 - ((yy - h / 2.1) / (h / 3.0)) ** 2 - ((xx - w / 1.9) / (w / 4.0)) ** 2, 0, None), 0, 65535),
+        "two_level": np.where(rng.random((h, w)) < 0.999, 100, 65535),
+        "low_outlier": np.where(rng.random((h, w)) < 0.002, 0, rng.integers(30000, 30100, (h, w))),
+    }
+    return {k: v.astype(np.uint16) for k, v in out.items()}

@@ -1,0 +1,280 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same inputs.
+Bit-exact for integer outputs, percentiles and GLCM bins; 1e-9 relative (north_star allows 1e-5)
+for floating-point statistics and Haralick features."""
+import numpy as np
+import pytest
+
+import imfeat_b200 as imf
+from conftest import compare_tables, parity_distributions
+from oracle import c_oracle
+from oracle import notebook_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _planar(img):
+    return np.ascontiguousarray(np.asarray(img).transpose(0, 3, 1, 2))
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    return torch
+
+
+def test_golden_fixtures(golden, torch_mod):
+    """Reference-generated vectors (tests/golden/make_golden.py) through extract_features."""
+    for name, (img, want, cols) in golden.items():
+        got = imf.extract_features(img[None])
+        assert imf.feature_columns(img.shape[2]) == cols
+        compare_tables(got, want[None], cols, label=name)
+
+
+def test_reference_shaped_functions(golden, torch_mod):
+    img, want, cols = golden["mix_64x64x4"]
+    d = imf.basic_statistical_features(img)            # NB:362
+    g = imf.glcm_features(img)                         # NB:363
+    feats = {}
+    feats.update(d)
+    feats.update(g)
+    assert list(feats.keys()) == cols
+    compare_tables(np.array([list(feats.values())]), want[None], cols, label="dicts")
+    frame = imf.extract_features(img[None], as_frame=True)
+    assert list(frame.columns) == cols
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (37, 91), (128, 128), (9, 5), (7, 6), (1, 1), (33, 17),
+                                   (3, 300), (181, 181), (2, 16384)])
+def test_distributions_all_blocks(shape, torch_mod):
+    h, w = shape
+    rng = np.random.default_rng(h * 1000 + w)
+    d = parity_distributions(rng, h, w)
+    names = sorted(d)
+    img = np.stack([d[k] for k in names], axis=2)[None]
+    want = c_oracle.table(_planar(img), glcm=True, n_angles=4, shape=True, moments=True)
+    got, status = imf.extract_features(img, four_directions=True, shape=True, moments=True,
+                                       return_status=True)
+    cols = imf.feature_columns(len(names), n_angles=4, shape=True, moments=True)
+    compare_tables(got, want, cols, label=str(shape))
+    if h * w > 1:
+        assert status[0] & 4          # constant channels present
+    # notebook-default call
+    want = c_oracle.table(_planar(img))
+    got = imf.extract_features(img)
+    compare_tables(got, want, imf.feature_columns(len(names)), label="default " + str(shape))
+
+
+def test_against_numpy_oracle_directly(torch_mod):
+    """Small case checked against the numpy restatement itself (not the C port)."""
+    rng = np.random.default_rng(3)
+    d = parity_distributions(rng, 48, 40)
+    img = np.stack([d[k] for k in sorted(d)], axis=2)
+    want, cols = orc.oracle_extract([img], glcm=True, four_directions=True, shape=True, moments=True)
+    got = imf.extract_features(img[None], four_directions=True, shape=True, moments=True)
+    compare_tables(got, want, cols, label="numpy oracle")
+
+
+def test_glcm_bins_bit_exact(torch_mod):
+    torch = torch_mod
+    rng = np.random.default_rng(11)
+    for (h, w) in [(64, 64), (33, 47), (128, 128), (9, 5)]:
+        d = parity_distributions(rng, h, w)
+        names = sorted(d)
+        img = np.stack([d[k] for k in names], axis=2)[None]
+        ex = imf.get_extractor(four_directions=True)
+        planes = torch.from_numpy(_planar(img)).cuda()
+        counts = ex.glcm_counts(planes).cpu().numpy().view(np.uint32)
+        for c, k in enumerate(names):
+            want = orc.glcm_counts(d[k], angles=orc.ANGLES4)
+            for a in range(4):
+                assert (counts[0, c, a] == want[:, :, a]).all(), (h, w, k, a)
+        # masked bins
+        mask = (rng.random((1, h, w, len(names))) < 0.7).astype(np.uint8)
+        counts = ex.glcm_counts(planes, torch.from_numpy(_planar(mask)).cuda()).cpu().numpy().view(np.uint32)
+        for c, k in enumerate(names):
+            want = c_oracle.glcm_counts(d[k], mask[0, :, :, c], n_angles=4)
+            assert (counts[0, c] == want).all(), ("masked", h, w, k)
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (37, 91), (128, 128), (20, 9)])
+def test_masked_all_blocks(shape, torch_mod):
+    h, w = shape
+    rng = np.random.default_rng(77 + h)
+    d = parity_distributions(rng, h, w)
+    names = sorted(d)
+    img = np.stack([d[k] for k in names], axis=2)[None]
+    yy, xx = np.mgrid[0:h, 0:w]
+    masks = []
+    for k in range(len(names)):
+        m = ((yy - h / 2) ** 2 / (h / (2.2 + 0.3 * k)) ** 2 + (xx - w / 2) ** 2 / (w / 2.5) ** 2) < 1
+        if k == 3:
+            m = np.zeros_like(m)
+        if k == 4:
+            m = np.ones_like(m)
+        if k == 5:
+            m = rng.random((h, w)) < 0.05         # sparse, disconnected
+        masks.append(m)
+    mask = np.stack(masks, axis=2).astype(np.uint8)[None]
+    want = c_oracle.table(_planar(img), _planar(mask), glcm=True, n_angles=4, shape=True, moments=True)
+    got, status = imf.extract_features(img, mask, four_directions=True, shape=True, moments=True,
+                                       return_status=True)
+    cols = imf.feature_columns(len(names), n_angles=4, shape=True, moments=True)
+    compare_tables(got, want, cols, label="masked " + str(shape))
+    assert status[0] & 1              # the empty mask was flagged
+    # mask values other than 0/1 count as inside
+    got2 = imf.extract_features(img, mask * 200, four_directions=True, shape=True, moments=True)
+    assert np.array_equal(got, got2, equal_nan=True)
+
+
+def test_variable_sizes(torch_mod):
+    rng = np.random.default_rng(5)
+    objs, masks = [], []
+    for i in range(24):
+        h, w = int(rng.integers(6, 129)), int(rng.integers(6, 129))
+        objs.append(rng.integers(0, 4096, (h, w, 5)).astype(np.uint16))
+        masks.append((rng.random((h, w, 5)) < 0.5).astype(np.uint8))
+    got = imf.extract_features(objs, four_directions=True, shape=True, moments=True)
+    gotm = imf.extract_features(objs, masks, four_directions=True, shape=True, moments=True)
+    cols = imf.feature_columns(5, n_angles=4, shape=True, moments=True)
+    for i, (o, m) in enumerate(zip(objs, masks)):
+        want = c_oracle.table(_planar(o[None]), glcm=True, n_angles=4, shape=True, moments=True)
+        compare_tables(got[i:i + 1], want, cols, label="var %d %s" % (i, o.shape))
+        want = c_oracle.table(_planar(o[None]), _planar(m[None]), glcm=True, n_angles=4, shape=True, moments=True)
+        compare_tables(gotm[i:i + 1], want, cols, label="var masked %d %s" % (i, o.shape))
+
+
+def test_synth_device_matches_numpy_mirror(torch_mod):
+    from imfeat_b200 import synth
+    ex = imf.get_extractor()
+    planes, masks, _ = ex.synth(123, 40, 6, 3, 64, 64, with_masks=True)
+    planes, masks = planes.cpu().numpy(), masks.cpu().numpy()
+    for i in range(6):
+        for ch in range(3):
+            p, m = synth.synth_plane(123, 40 + i, ch, 64, 64)
+            assert (planes[i, ch, :4096].reshape(64, 64) == p).all()
+            assert (masks[i, ch, :4096].reshape(64, 64) == m).all()
+    planes, masks, sizes = ex.synth(9, 0, 10, 2, 128, 128, with_masks=True, variable=True, hmin=16,
+                                    wmin=16, mask_shrink=40)
+    planes, masks, sizes = planes.cpu().numpy(), masks.cpu().numpy(), sizes.cpu().numpy()
+    for i in range(10):
+        h, w = synth.object_size(9, i, 128, 128, True, 16, 16)
+        assert tuple(sizes[i]) == (h, w)
+        for ch in range(2):
+            p, m = synth.synth_plane(9, i, ch, h, w, mask_shrink=40)
+            assert (planes[i, ch, :h * w].reshape(h, w) == p).all()
+            assert (masks[i, ch, :h * w].reshape(h, w) == m).all()
+
+
+def test_synthetic_batch_parity(torch_mod):
+    """cfg1/cfg2 inputs (64x64x12 + masks), 256 objects, every block, against the C oracle."""
+    from imfeat_b200 import synth
+    img, mask = synth.synth_batch_hwc(0, 0, 256, 12, 64, 64)
+    cols = imf.feature_columns(12, n_angles=4, shape=True, moments=True)
+    want = c_oracle.table(_planar(img), _planar(mask), glcm=True, n_angles=4, shape=True, moments=True)
+    got = imf.extract_features(img, mask, four_directions=True, shape=True, moments=True)
+    compare_tables(got, want, cols, label="synthetic masked")
+    want = c_oracle.table(_planar(img))
+    got = imf.extract_features(img)
+    compare_tables(got, want, imf.feature_columns(12), label="synthetic notebook mode")
+
+
+def test_host_and_device_paths_agree(torch_mod):
+    torch = torch_mod
+    from imfeat_b200 import synth
+    img, mask = synth.synth_batch_hwc(1, 0, 64, 12, 64, 64)
+    ex = imf.get_extractor(four_directions=True)
+    host = ex.extract_host_hwc(img, mask)
+    planes, pmasks, hs, ws = ex.pack_hwc(torch.from_numpy(img).cuda(), torch.from_numpy(mask).cuda())
+    dev = ex.extract_planar(planes, pmasks, hs=hs, ws=ws).cpu().numpy()
+    assert np.array_equal(host, dev, equal_nan=True)
+    host_planar = ex.extract_host_planar(_planar(img), _planar(mask))
+    assert np.array_equal(host, host_planar, equal_nan=True)
+    # device-generated objects == host mirror objects
+    dplanes, dmasks, _ = ex.synth(1, 0, 64, 12, 64, 64)
+    dev2 = ex.extract_planar(dplanes, dmasks, hs=64, ws=64).cpu().numpy()
+    assert np.array_equal(host, dev2, equal_nan=True)
+
+
+def test_channel_selection_and_ablation_indirection(torch_mod):
+    """LOCO == dropping that channel's columns; per-channel object permutation == permuting the
+    rows of that channel's column blocks (features are per-channel independent, NB:239/291)."""
+    torch = torch_mod
+    from imfeat_b200 import schema
+    ex = imf.get_extractor(four_directions=False)
+    C, N = 6, 48
+    planes, masks, _ = ex.synth(5, 0, N, C, 64, 64)
+    base = ex.extract_planar(planes, masks, hs=64, ws=64).cpu().numpy()
+    for drop in (0, 3, 5):
+        keep = [c for c in range(C) if c != drop]
+        chan = torch.tensor(keep, dtype=torch.int32, device="cuda")
+        t = ex.extract_planar(planes, masks, hs=64, ws=64, chan=chan).cpu().numpy()
+        idx = []
+        for pos, c in enumerate(keep):
+            idx.append((schema.channel_column_index(C - 1, pos), schema.channel_column_index(C, c)))
+        for sub, full in idx:
+            assert np.array_equal(t[:, sub], base[:, full], equal_nan=True)
+    perm = np.random.default_rng(42).permutation(N).astype(np.int32)
+    for ch in (1, 4):
+        src = np.tile(np.arange(N, dtype=np.int32)[:, None], (1, C))
+        src[:, ch] = perm
+        t = ex.extract_planar(planes, masks, hs=64, ws=64,
+                              src_obj=torch.from_numpy(src).cuda()).cpu().numpy()
+        want = base.copy()
+        cidx = schema.channel_column_index(C, ch)
+        want[:, cidx] = base[perm][:, cidx]
+        assert np.array_equal(t, want, equal_nan=True)
+    # channels= on the functional API
+    img, _ = __import__("imfeat_b200").synth.synth_batch_hwc(5, 0, 4, C, 64, 64)
+    sel = imf.extract_features(img, channels=[4, 1])
+    full = imf.extract_features(img)
+    assert np.array_equal(sel[:, schema.channel_column_index(2, 0)], full[:, schema.channel_column_index(C, 4)])
+    assert np.array_equal(sel[:, schema.channel_column_index(2, 1)], full[:, schema.channel_column_index(C, 1)])
+
+
+def test_argument_errors(torch_mod):
+    with pytest.raises(TypeError):
+        imf.extract_features(np.zeros((1, 8, 8, 2), np.float32) + 0.5)
+    with pytest.raises(imf.ImfeatError):
+        imf.extract_features(np.zeros((1, 256, 256, 1), np.uint16))     # > IMFEAT_MAX_PIXELS
+    ex = imf.get_extractor()
+    import torch
+    planes = torch.zeros((2, 3, 64, 64), dtype=torch.uint16, device="cuda")
+    with pytest.raises(imf.ImfeatError):
+        ex.extract_planar(planes, out=torch.empty((2, 10), dtype=torch.float64, device="cuda"))
+    empty = ex.extract_planar(planes[:0])
+    assert empty.shape == (0, 69)
+
+
+def test_full_size_properties(torch_mod):
+    """cfg2 at BASELINE size (10,000 objects): size-independent properties + sampled parity."""
+    torch = torch_mod
+    ex = imf.get_extractor(four_directions=True)
+    N, C = 10000, 12
+    planes, masks, _ = ex.synth(0, 0, N, C, 64, 64)
+    t = ex.extract_planar(planes, None, hs=64, ws=64).cpu().numpy()
+    cols = ex.columns(C)
+    col = {c: i for i, c in enumerate(cols)}
+    for ch in (1, 7, 12):
+        g = lambda name: t[:, col["%s_Ch%d" % (name, ch)]]
+        assert np.array_equal(g("mean_intensity"), g("total_intensity") / 4096.0)
+        assert (g("min_intensity") <= g("percentile10_intensity")).all()
+        assert (np.diff(np.stack([g("percentile%d0_intensity" % k) for k in range(1, 10)]), axis=0) >= 0).all()
+        assert (g("percentile90_intensity") <= g("max_intensity")).all()
+        assert ((g("shannon_entropy") > 0) & (g("shannon_entropy") <= 12.0)).all()
+        for tag in ("", "_a45", "_a90", "_a135"):
+            a = t[:, col["ASM%s_Ch%d" % (tag, ch)]]
+            e = t[:, col["energy%s_Ch%d" % (tag, ch)]]
+            np.testing.assert_allclose(e * e, a, rtol=1e-12)
+            corr = t[:, col["correlation%s_Ch%d" % (tag, ch)]]
+            assert (np.abs(corr) <= 1 + 1e-12).all()
+    # idempotence / order independence: reversed object order gives the reversed table
+    t2 = ex.extract_planar(planes.flip(0).contiguous(), None, hs=64, ws=64).cpu().numpy()
+    assert np.array_equal(t2[::-1], t, equal_nan=True)
+    # sampled parity on regenerated objects (host mirror of the device generator)
+    from imfeat_b200 import synth
+    pick = np.random.default_rng(0).choice(N, 48, replace=False)
+    for i in pick:
+        img = np.stack([synth.synth_plane(0, int(i), ch, 64, 64)[0] for ch in range(C)], axis=2)[None]
+        want = c_oracle.table(_planar(img), glcm=True, n_angles=4)
+        compare_tables(t[i:i + 1], want, cols, label="sample %d" % i)
