@@ -40,6 +40,19 @@ def plane_stride_for(hs, ws):
     return (hs * ws + 7) & ~7
 
 
+def _planes3(t):
+    """[N, C, Hs, Ws] -> ([N, C, plane_stride], hs, ws); pads the plane to a multiple of 8
+    elements when Hs*Ws is not one (the C ABI wants 16-byte aligned planes)."""
+    torch = _torch()
+    N, C, hs, ws = (int(v) for v in t.shape)
+    stride = plane_stride_for(hs, ws)
+    if stride == hs * ws:
+        return t.reshape(N, C, stride), hs, ws
+    p = torch.zeros((N, C, stride), dtype=t.dtype, device=t.device)
+    p[:, :, :hs * ws] = t.reshape(N, C, hs * ws)
+    return p, hs, ws
+
+
 class FeatureExtractor:
     """One context (lookup tables, staging buffers) on one GPU + a fixed option set.
 
@@ -117,13 +130,12 @@ class FeatureExtractor:
         Returns a cuda float64 [N, row_width] table (``out`` is reused when given)."""
         torch = _torch()
         assert planes.is_cuda and planes.is_contiguous() and planes.element_size() == 2
-        N, C = int(planes.shape[0]), int(planes.shape[1])
         if planes.dim() == 4:
-            hs, ws = int(planes.shape[2]), int(planes.shape[3])
-            stride = hs * ws
-        else:
-            assert hs is not None and ws is not None
-            stride = int(planes.shape[2])
+            planes, hs, ws = _planes3(planes)
+            if masks is not None and masks.dim() == 4:
+                masks = _planes3(masks)[0]
+        assert hs is not None and ws is not None
+        N, C, stride = (int(v) for v in planes.shape)
         if masks is not None:
             assert masks.is_cuda and masks.is_contiguous() and masks.element_size() == 1
             assert masks.numel() == planes.numel()
@@ -159,12 +171,11 @@ class FeatureExtractor:
     def glcm_counts(self, planes, masks=None, sizes=None, hs=None, ws=None, stream=None):
         """Raw GLCM bins (NB:298): cuda int32 [N, C, n_angles, 256, 256] (values are uint32)."""
         torch = _torch()
-        N, C = int(planes.shape[0]), int(planes.shape[1])
         if planes.dim() == 4:
-            hs, ws = int(planes.shape[2]), int(planes.shape[3])
-            stride = hs * ws
-        else:
-            stride = int(planes.shape[2])
+            planes, hs, ws = _planes3(planes)
+            if masks is not None and masks.dim() == 4:
+                masks = _planes3(masks)[0]
+        N, C, stride = (int(v) for v in planes.shape)
         counts = torch.empty((N, C, self.n_angles, 256, 256), dtype=torch.int32, device=planes.device)
         _lib.check(self.lib.imfeat_glcm_counts_device(
             self._ctx, _ptr(planes), _ptr(masks), _ptr(sizes), N, C, hs, ws, stride,
