@@ -28,6 +28,7 @@ struct Params {
     double* out;
     uint32_t* status;          // nullable
     const double* log2tab;     // log2(k), k = 0..kMaxPixels (k=0 -> 0)
+    const unsigned long long* gfix;  // round(2^42 * ((k+1)*log2(k+1) - k*log2(k))), k < kMaxPixels
     uint32_t* counts;          // nullable: GLCM bin dump [tile][angle][65536]
     long long n_tiles;
     long long plane_stride;
@@ -86,6 +87,27 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// Named barriers (ids 1..15; 0 is __syncthreads).  bar_arrive + bar_sync on the same id is the
+// producer/consumer hand-off: the arriving threads' prior shared-memory writes are visible to the
+// threads released by bar_sync.
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Two thread groups per CTA share one 128 KB shared-memory table in turns ("ping-pong"): while one
+// group owns the table (atomics -> read -> sparse clear), the other does its table-free work
+// (loads, reductions, epilogues) for the next tile.  Barrier ids: 1+g group-internal,
+// 3+g "table is free for group g".
+constexpr int kGroupThreads = 512;
+constexpr int kGroupWarps = kGroupThreads / 32;
+constexpr int kPingPongThreads = 2 * kGroupThreads;
+__device__ __forceinline__ void group_sync(int g) { bar_sync(1 + g, kGroupThreads); }
+__device__ __forceinline__ void table_acquire(int g) { bar_sync(3 + g, kPingPongThreads); }
+__device__ __forceinline__ void table_release(int g) { bar_arrive(3 + (g ^ 1), kPingPongThreads); }
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 

@@ -26,6 +26,7 @@ struct imfeat_ctx {
     int device;
     int sm_count;
     double* d_log2tab;
+    unsigned long long* d_gfix;
     long long launches;
     char err[512];
     // host-path staging (lazily sized)
@@ -119,6 +120,18 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
     cudaError_t e = cudaMalloc(&ctx->d_log2tab, sizeof(double) * (kMaxPixels + 1));
     if (e == cudaSuccess)
         e = cudaMemcpy(ctx->d_log2tab, tab, sizeof(double) * (kMaxPixels + 1), cudaMemcpyHostToDevice);
+    // G[k] = (k+1)*log2(k+1) - k*log2(k) in 2^-42 fixed point (extended precision, rounded once);
+    // G < 16.5, so a sum over kMaxPixels terms stays below 2^63
+    unsigned long long* gfix = (unsigned long long*)tab;
+    static_assert(sizeof(unsigned long long) == sizeof(double), "table reuse");
+    for (int k = 0; k < kMaxPixels; ++k) {
+        const long double a = (long double)(k + 1) * log2l((long double)(k + 1));
+        const long double b = k ? (long double)k * log2l((long double)k) : 0.0L;
+        gfix[k] = (unsigned long long)llroundl((a - b) * 4398046511104.0L);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_gfix, sizeof(unsigned long long) * kMaxPixels);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(ctx->d_gfix, gfix, sizeof(unsigned long long) * kMaxPixels, cudaMemcpyHostToDevice);
     free(tab);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_order_entropy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_order_entropy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
@@ -131,6 +144,7 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
     if (e != cudaSuccess) {
         int rc = fail(nullptr, IMFEAT_ERR_CUDA, "context set-up failed: %s", cudaGetErrorString(e));
         if (ctx->d_log2tab) cudaFree(ctx->d_log2tab);
+        if (ctx->d_gfix) cudaFree(ctx->d_gfix);
         free(ctx);
         return rc;
     }
@@ -161,6 +175,7 @@ int imfeat_destroy(imfeat_ctx* ctx) {
         for (int k = 0; k < 5; ++k)
             if (ctx->t_ev[sl][k]) cudaEventDestroy(ctx->t_ev[sl][k]);
     if (ctx->d_log2tab) cudaFree(ctx->d_log2tab);
+    if (ctx->d_gfix) cudaFree(ctx->d_gfix);
     free(ctx);
     return IMFEAT_OK;
 }
@@ -199,7 +214,7 @@ static void fill_params(Params& P, imfeat_ctx* ctx, const uint16_t* planes, cons
                         const imfeat_opts* o, double* out, int64_t row_stride, uint32_t* status) {
     memset(&P, 0, sizeof(P));
     P.planes = planes; P.masks = masks; P.sizes = sizes; P.src_obj = src_obj; P.chan = chan;
-    P.out = out; P.status = status; P.log2tab = ctx->d_log2tab; P.counts = nullptr;
+    P.out = out; P.status = status; P.log2tab = ctx->d_log2tab; P.gfix = ctx->d_gfix; P.counts = nullptr;
     P.n_tiles = n * c_out; P.plane_stride = plane_stride; P.row_stride = row_stride;
     P.c_in = c_in; P.c_out = c_out; P.hs = hs; P.ws = ws;
     int col = 0;
@@ -266,15 +281,15 @@ static int launch_all(imfeat_ctx* ctx, const Params& P, const imfeat_opts* o, cu
         else k1_moments_kernel<false><<<g1, 256, 0, st>>>(P);
         IMFEAT_MARK(0)
         const int g2 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
-        if (masked) k2_order_entropy_kernel<true><<<g2, kK2Threads, sizeof(K2Smem), st>>>(P);
-        else k2_order_entropy_kernel<false><<<g2, kK2Threads, sizeof(K2Smem), st>>>(P);
+        if (masked) k2_order_entropy_kernel<true><<<g2, kPingPongThreads, sizeof(K2Smem), st>>>(P);
+        else k2_order_entropy_kernel<false><<<g2, kPingPongThreads, sizeof(K2Smem), st>>>(P);
         IMFEAT_MARK(1)
         ctx->launches += 2;
     }
     if (o->want_glcm) {
         const int g3 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
-        if (masked) k3_glcm_kernel<true, false><<<g3, kK3Threads, sizeof(K3Smem), st>>>(P);
-        else k3_glcm_kernel<false, false><<<g3, kK3Threads, sizeof(K3Smem), st>>>(P);
+        if (masked) k3_glcm_kernel<true, false><<<g3, kPingPongThreads, sizeof(K3Smem), st>>>(P);
+        else k3_glcm_kernel<false, false><<<g3, kPingPongThreads, sizeof(K3Smem), st>>>(P);
         IMFEAT_MARK(2)
         ctx->launches += 1;
     }
@@ -359,8 +374,8 @@ int imfeat_glcm_counts_device(imfeat_ctx* ctx, const uint16_t* d_planes, const u
                 plane_stride, &o, scratch, width, nullptr);
     P.counts = d_counts;
     const int g3 = (int)(P.n_tiles < ctx->sm_count ? P.n_tiles : ctx->sm_count);
-    if (d_masks) k3_glcm_kernel<true, true><<<g3, kK3Threads, sizeof(K3Smem), st>>>(P);
-    else k3_glcm_kernel<false, true><<<g3, kK3Threads, sizeof(K3Smem), st>>>(P);
+    if (d_masks) k3_glcm_kernel<true, true><<<g3, kPingPongThreads, sizeof(K3Smem), st>>>(P);
+    else k3_glcm_kernel<false, true><<<g3, kPingPongThreads, sizeof(K3Smem), st>>>(P);
     ctx->launches += 1;
     CU(cudaGetLastError());
     CU(cudaFreeAsync(scratch, st));

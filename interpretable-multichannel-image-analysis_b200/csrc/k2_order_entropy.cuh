@@ -1,76 +1,105 @@
-// k2_order_entropy.cuh -- K2: order statistics + Shannon entropy, one CTA per tile.
+// k2_order_entropy.cuh -- K2: order statistics + Shannon entropy.
 //
 // Replaces, per channel:  np.percentile(X, 0.1 .. 0.9)  NB:242-250   shannon_entropy(X)  NB:262
 //
-// Both need the multiplicity of every raw 16-bit value in the tile.  The CTA keeps a
-// privatised 65,536-bin histogram in shared memory (16-bit counters, two per word, 128 KB),
-// built with shared-memory atomics, plus a 1,024-bit "occupied 64-value block" bitmap.
-//   entropy      H = (1/n) * sum_pixels (log2 n - log2 c[x_p])        (no pass over the bins)
-//   percentiles  one warp walks only the occupied blocks from the bottom until the needed
-//                ranks are covered, then applies numpy's linear-interpolation formula
-//   clear        by re-walking the pixels, never densely
+// Both need the multiplicity of every raw 16-bit value of the tile.  The CTA owns one privatised
+// 65,536-bin histogram in shared memory (16-bit counters, two per word, 128 KB) plus a 1,024-bit
+// "occupied 64-value block" bitmap.  Two 512-thread groups work on two tiles at a time and take
+// turns on the table (common.cuh, "ping-pong").
+//   entropy      sum_values c*log2(c) telescopes over the atomics' return values:
+//                sum_pixels G[old_p],  G[k] = (k+1)log2(k+1) - k*log2(k)   -> no read-back pass.
+//                G is held in 2^-42 fixed point and summed in 64-bit integers, so the result
+//                does not depend on the order in which the atomics resolve (bit-reproducible)
+//   percentiles  one warp walks only the occupied blocks from the bottom until the needed ranks
+//                are covered, then applies numpy's linear-interpolation formula bit for bit
+//   clear        by re-walking the pixels (registers), never densely
 #pragma once
 #include "common.cuh"
 
 namespace imfeat {
 
-constexpr int kK2Threads = 512;
-constexpr int kK2Warps = kK2Threads / 32;
+constexpr int kK2Vec = 2;      // 16-byte vectors per thread kept in registers (n <= 8192)
 
+struct K2Group {
+    int vals[18];
+    uint32_t wcnt[kGroupWarps];
+    unsigned long long wpart[kGroupWarps];
+    int constant;
+};
 struct K2Smem {
     uint32_t hist[32768];
     uint32_t coarse[32];
-    int vals[18];
-    uint32_t wcnt[kK2Warps];
-    double wpart[kK2Warps];
+    K2Group grp[2];
 };
 
-__device__ __forceinline__ void k2_add(K2Smem& S, uint32_t x) {
-    atomicAdd(&S.hist[x >> 1], 1u << ((x & 1u) << 4));
+// returns the count of x BEFORE this increment
+__device__ __forceinline__ uint32_t k2_add(K2Smem& S, uint32_t x) {
+    const uint32_t sh = (x & 1u) << 4;
+    const uint32_t old = atomicAdd(&S.hist[x >> 1], 1u << sh);
     const uint32_t b = x >> 6, bit = 1u << (b & 31u);
     if (!(*(volatile uint32_t*)&S.coarse[b >> 5] & bit)) atomicOr(&S.coarse[b >> 5], bit);
-}
-__device__ __forceinline__ uint32_t k2_count(const K2Smem& S, uint32_t x) {
-    return (S.hist[x >> 1] >> ((x & 1u) << 4)) & 0xffffu;
+    return (old >> sh) & 0xffffu;
 }
 
-// PHASE 0: histogram build, 1: entropy read-back, 2: sparse clear.
+// PHASE 0: histogram build + entropy terms, 2: sparse clear.
 template <int PHASE, bool MASKED>
-__device__ __forceinline__ void k2_px(K2Smem& S, const Params& P, uint32_t x, bool ok,
-                                      uint32_t& cnt, double& acc, double log2n) {
-    if (MASKED && !ok) return;
-    if (PHASE == 0) { k2_add(S, x); if (MASKED) ++cnt; }
-    if (PHASE == 1) acc += log2n - __ldg(P.log2tab + k2_count(S, x));
-    if (PHASE == 2) S.hist[x >> 1] = 0u;
+__device__ __forceinline__ void k2_vec(K2Smem& S, const Params& P, const uint4& v, const uint2& m,
+                                       uint32_t& cnt, uint32_t& maxold, unsigned long long& acc) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t mb = (k < 2 ? m.x : m.y) >> (16 * (k & 1));
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+            const uint32_t x = hlf ? (w[k] >> 16) : (w[k] & 0xffffu);
+            if (MASKED && !(mb & (hlf ? 0xff00u : 0xffu))) continue;
+            if (PHASE == 0) {
+                const uint32_t old = k2_add(S, x);
+                acc += __ldg(P.gfix + old);
+                maxold = max(maxold, old);
+                if (MASKED) ++cnt;
+            } else {
+                S.hist[x >> 1] = 0u;
+            }
+        }
+    }
 }
 
 template <int PHASE, bool MASKED>
-__device__ __forceinline__ void k2_walk(K2Smem& S, const Params& P, const Tile& T, uint32_t& cnt,
-                                        double& acc, double log2n) {
+__device__ __forceinline__ void k2_walk(K2Smem& S, const Params& P, const Tile& T, int gt,
+                                        const uint4* vreg, const uint2* mreg, uint32_t& cnt,
+                                        uint32_t& maxold, unsigned long long& acc) {
     const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
     const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
     const int nfull = T.n >> 3, rem = T.n & 7;
-    for (int idx = threadIdx.x; idx < nfull; idx += kK2Threads) {
-        const uint4 v = ld_reuse(px4 + idx);
-        uint2 m = make_uint2(0x01010101u, 0x01010101u);
-        if (MASKED) m = __ldg(mk2 + idx);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t mb = (k < 2 ? m.x : m.y) >> (16 * (k & 1));
-            k2_px<PHASE, MASKED>(S, P, w[k] & 0xffffu, (mb & 0xffu) != 0, cnt, acc, log2n);
-            k2_px<PHASE, MASKED>(S, P, w[k] >> 16, (mb & 0xff00u) != 0, cnt, acc, log2n);
-        }
+    for (int i = 0; i < kK2Vec; ++i)
+        if (gt + i * kGroupThreads < nfull) k2_vec<PHASE, MASKED>(S, P, vreg[i], mreg[i], cnt, maxold, acc);
+    for (int idx = gt + kK2Vec * kGroupThreads; idx < nfull; idx += kGroupThreads) {
+        const uint4 v = ld_reuse(px4 + idx);
+        uint2 m = make_uint2(0u, 0u);
+        if (MASKED) m = __ldg(mk2 + idx);
+        k2_vec<PHASE, MASKED>(S, P, v, m, cnt, maxold, acc);
     }
-    if ((int)threadIdx.x < rem) {
-        const int i = nfull * 8 + threadIdx.x;
-        k2_px<PHASE, MASKED>(S, P, T.px[i], !MASKED || T.mk[i] != 0, cnt, acc, log2n);
+    if (gt < rem) {
+        const int i = nfull * 8 + gt;
+        if (!MASKED || T.mk[i] != 0) {
+            const uint32_t x = T.px[i];
+            if (PHASE == 0) {
+                const uint32_t old = k2_add(S, x);
+                acc += __ldg(P.gfix + old);
+                maxold = max(maxold, old);
+                if (MASKED) ++cnt;
+            } else {
+                S.hist[x >> 1] = 0u;
+            }
+        }
     }
 }
 
-// Warp 0: numpy percentile (method "linear") from the histogram; ranks are 0-based positions
+// One warp: numpy percentile (method "linear") from the histogram; ranks are 0-based positions
 // in the sorted multiset.
-__device__ __forceinline__ void k2_percentiles(K2Smem& S, const Params& P, int n, double* o) {
+__device__ __forceinline__ void k2_percentiles(K2Smem& S, int* vals, const Params& P, int n, double* o) {
     const int lane = threadIdx.x & 31;
     int lo[9], hi[9], maxrank = 0;
 #pragma unroll
@@ -100,8 +129,8 @@ __device__ __forceinline__ void k2_percentiles(K2Smem& S, const Params& P, int n
             const int base = block * 64 + 2 * lane;
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                if (lo[k] >= r0 && lo[k] < r1) S.vals[2 * k] = base + (lo[k] >= r0 + c0);
-                if (hi[k] >= r0 && hi[k] < r1) S.vals[2 * k + 1] = base + (hi[k] >= r0 + c0);
+                if (lo[k] >= r0 && lo[k] < r1) vals[2 * k] = base + (lo[k] >= r0 + c0);
+                if (hi[k] >= r0 && hi[k] < r1) vals[2 * k + 1] = base + (hi[k] >= r0 + c0);
             }
             cum += __shfl_sync(0xffffffffu, incl, 31);
             if (cum > maxrank) { done = true; break; }
@@ -111,7 +140,7 @@ __device__ __forceinline__ void k2_percentiles(K2Smem& S, const Params& P, int n
     if (lane < 9) {
         const double virt = __dmul_rn((double)(n - 1), P.quant[lane]);
         const double g = virt - floor(virt);
-        const int a = S.vals[2 * lane], b = S.vals[2 * lane + 1];
+        const int a = vals[2 * lane], b = vals[2 * lane + 1];
         const double diff = (double)(b - a);
         // numpy _lerp: a + diff*t, replaced by b - diff*(1-t) where t >= 0.5 (no FMA there)
         const double r = (g >= 0.5) ? __dsub_rn((double)b, __dmul_rn(diff, __dsub_rn(1.0, g)))
@@ -121,57 +150,90 @@ __device__ __forceinline__ void k2_percentiles(K2Smem& S, const Params& P, int n
 }
 
 template <bool MASKED>
-__global__ void __launch_bounds__(kK2Threads, 1) k2_order_entropy_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(kPingPongThreads, 1) k2_order_entropy_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) unsigned char k2_smem_raw[];
     K2Smem& S = *reinterpret_cast<K2Smem*>(k2_smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, g = tid / kGroupThreads, gt = tid % kGroupThreads;
+    const int lane = tid & 31, gw = gt >> 5;
+    K2Group& G = S.grp[g];
 
-    for (int k = tid; k < 32768; k += kK2Threads) S.hist[k] = 0u;
+    for (int k = tid; k < 32768; k += kPingPongThreads) S.hist[k] = 0u;
     if (tid < 32) S.coarse[tid] = 0u;
+    if (gt == 0) G.constant = 0;
     __syncthreads();
+    if (g == 1) table_release(1);                          // the table starts out free for group 0
 
-    for (long long t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
-        const Tile T = resolve_tile(P, t);
-        double* o = T.out_row + P.col_basic + kNBasic * T.slot;
-        uint32_t cnt = 0;
-        double acc = 0.0;
-
-        k2_walk<0, MASKED>(S, P, T, cnt, acc, 0.0);
-        if (MASKED) {
-            cnt = __reduce_add_sync(0xffffffffu, cnt);
-            if (lane == 0) S.wcnt[warp] = cnt;
-        }
-        __syncthreads();                                   // histogram complete
-        int n = T.n;
-        if (MASKED) {
-            n = 0;
+    const long long first = blockIdx.x;
+    const long long mine = first < P.n_tiles ? (P.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
+    const long long n_iter = (mine + 1) / 2;
+    for (long long it = 0; it < n_iter; ++it) {
+        const long long k = 2 * it + g;
+        const bool active = k < mine;
+        Tile T;
+        double* o = nullptr;
+        uint4 vreg[kK2Vec];
+        uint2 mreg[kK2Vec];
+        uint32_t cnt = 0, maxold = 0;
+        unsigned long long acc = 0ull;
+        if (active) {
+            T = resolve_tile(P, first + k * gridDim.x);
+            o = T.out_row + P.col_basic + kNBasic * T.slot;
+            const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
+            const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
+            const int nfull = T.n >> 3;
 #pragma unroll
-            for (int k = 0; k < kK2Warps; ++k) n += (int)S.wcnt[k];
-        }
-        if (n > 0) {
-            if (warp == 0) k2_percentiles(S, P, n, o);
-            const double log2n = __ldg(P.log2tab + n);
-            k2_walk<1, MASKED>(S, P, T, cnt, acc, log2n);
-        }
-        acc = warp_sum(acc);
-        if (lane == 0) S.wpart[warp] = acc;
-        __syncthreads();                                   // all read-backs done
-        k2_walk<2, MASKED>(S, P, T, cnt, acc, 0.0);
-        if (tid < 32) S.coarse[tid] = 0u;
-        if (tid == 0) {
-            if (n > 0) {
-                double tot = 0.0;
-#pragma unroll
-                for (int k = 0; k < kK2Warps; ++k) tot += S.wpart[k];
-                o[16] = tot / (double)n;
-            } else {
-                const double nan = qnan();
-#pragma unroll
-                for (int k = 1; k <= 9; ++k) o[k] = nan;
-                o[16] = nan;
+            for (int i = 0; i < kK2Vec; ++i) {
+                const int idx = gt + i * kGroupThreads;
+                mreg[i] = make_uint2(0u, 0u);
+                if (idx < nfull) {
+                    vreg[i] = ld_stream(px4 + idx);
+                    if (MASKED) mreg[i] = __ldg(mk2 + idx);
+                }
             }
         }
-        __syncthreads();                                   // table clean for the next tile
+        table_acquire(g);                                  // ---- table owned by this group ----
+        int n = 0;
+        if (active) {
+            k2_walk<0, MASKED>(S, P, T, gt, vreg, mreg, cnt, maxold, acc);
+            if (MASKED) {
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                if (lane == 0) G.wcnt[gw] = cnt;
+            }
+            group_sync(g);                                 // histogram complete
+            n = T.n;
+            if (MASKED) {
+                n = 0;
+#pragma unroll
+                for (int w = 0; w < kGroupWarps; ++w) n += (int)G.wcnt[w];
+            }
+            if (n > 0 && (int)maxold + 1 == n) G.constant = 1;   // one value only: entropy is exactly 0
+            if (gw == 0 && n > 0) k2_percentiles(S, G.vals, P, n, o);
+            group_sync(g);                                 // percentile walk done
+            k2_walk<2, MASKED>(S, P, T, gt, vreg, mreg, cnt, maxold, acc);
+            if (gt < 32) S.coarse[gt] = 0u;
+        }
+        if (!(g == 1 && it == n_iter - 1)) table_release(g);   // ---- hand the table over ----
+        if (active) {
+            acc = warp_sum(acc);
+            if (lane == 0) G.wpart[gw] = acc;
+            group_sync(g);
+            if (gt == 0) {
+                if (n > 0) {
+                    unsigned long long tot = 0ull;
+#pragma unroll
+                    for (int w = 0; w < kGroupWarps; ++w) tot += G.wpart[w];
+                    // sum_values c*log2(c) = tot * 2^-42 ; H = log2 n - that / n
+                    const double H = __ldg(P.log2tab + n) - ((double)tot * 2.2737367544323206e-13) / (double)n;
+                    o[16] = G.constant ? 0.0 : H;
+                    G.constant = 0;
+                } else {
+                    const double nan = qnan();
+#pragma unroll
+                    for (int q = 1; q <= 9; ++q) o[q] = nan;
+                    o[16] = nan;
+                }
+            }
+        }
     }
 }
 
