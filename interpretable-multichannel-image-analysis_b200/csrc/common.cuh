@@ -50,8 +50,10 @@ struct Tile {
 
 __device__ __forceinline__ Tile resolve_tile(const Params& P, long long t) {
     Tile T;
-    const long long row = t / P.c_out;
-    const int slot = (int)(t - row * P.c_out);
+    // n_tiles < 2^31 is enforced by the host API: 32-bit division is much cheaper than 64-bit
+    const uint32_t row32 = (uint32_t)t / (uint32_t)P.c_out;
+    const long long row = row32;
+    const int slot = (int)((uint32_t)t - row32 * (uint32_t)P.c_out);
     const long long so = P.src_obj ? (long long)P.src_obj[t] : row;
     const int ch = P.chan ? P.chan[slot] : slot;
     T.h = P.sizes ? P.sizes[2 * so] : P.hs;

@@ -25,6 +25,7 @@ constexpr int kTimingSlots = 64;
 struct imfeat_ctx {
     int device;
     int sm_count;
+    int k1_bps[2], k4_bps[2];   // resident CTAs per SM (occupancy API), [masked]
     double* d_log2tab;
     unsigned long long* d_gfix;
     long long launches;
@@ -141,6 +142,10 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k4_shape_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k4_shape_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_bps[0], k1_moments_kernel<false>, 256, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_bps[1], k1_moments_kernel<true>, 256, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4_bps[0], k4_shape_kernel<false>, kK4Threads, sizeof(K4Smem));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4_bps[1], k4_shape_kernel<true>, kK4Threads, sizeof(K4Smem));
     if (e != cudaSuccess) {
         int rc = fail(nullptr, IMFEAT_ERR_CUDA, "context set-up failed: %s", cudaGetErrorString(e));
         if (ctx->d_log2tab) cudaFree(ctx->d_log2tab);
@@ -193,6 +198,8 @@ static int check_common(imfeat_ctx* ctx, const void* planes, int64_t n, int c_in
     if (n < 0) return fail(ctx, IMFEAT_ERR_ARG, "n_objects < 0");
     if (n > 0 && !planes) return fail(ctx, IMFEAT_ERR_ARG, "planes is NULL");
     if (c_in < 1 || c_out < 1) return fail(ctx, IMFEAT_ERR_ARG, "channel counts must be >= 1");
+    if (n * (int64_t)c_out >= ((int64_t)1 << 31))
+        return fail(ctx, IMFEAT_ERR_ARG, "n_objects * channels must be < 2^31 per call; split the batch");
     if (hs < 1 || ws < 1 || (int64_t)hs * ws > kMaxPixels)
         return fail(ctx, IMFEAT_ERR_ARG, "object size %dx%d outside 1..%d pixels per plane", hs, ws, kMaxPixels);
     if (plane_stride < (int64_t)hs * ws || (plane_stride & 7))
@@ -276,7 +283,8 @@ static int launch_all(imfeat_ctx* ctx, const Params& P, const imfeat_opts* o, cu
     const bool masked = P.masks != nullptr;
     const long long sm = ctx->sm_count;
     if (o->want_basic) {
-        const int g1 = (int)((P.n_tiles + 7) / 8 < sm * 8 ? (P.n_tiles + 7) / 8 : sm * 8);
+        const long long res1 = sm * (ctx->k1_bps[masked] > 0 ? ctx->k1_bps[masked] : 1);   // one resident wave
+        const int g1 = (int)((P.n_tiles + 7) / 8 < res1 ? (P.n_tiles + 7) / 8 : res1);
         if (masked) k1_moments_kernel<true><<<g1, 256, 0, st>>>(P);
         else k1_moments_kernel<false><<<g1, 256, 0, st>>>(P);
         IMFEAT_MARK(0)
@@ -294,7 +302,8 @@ static int launch_all(imfeat_ctx* ctx, const Params& P, const imfeat_opts* o, cu
         ctx->launches += 1;
     }
     if (o->want_shape || o->want_moments) {
-        const int g4 = (int)(P.n_tiles < sm * 3 ? P.n_tiles : sm * 3);
+        const long long res4 = sm * (ctx->k4_bps[masked] > 0 ? ctx->k4_bps[masked] : 1);
+        const int g4 = (int)(P.n_tiles < res4 ? P.n_tiles : res4);
         if (masked) k4_shape_kernel<true><<<g4, kK4Threads, sizeof(K4Smem), st>>>(P);
         else k4_shape_kernel<false><<<g4, kK4Threads, sizeof(K4Smem), st>>>(P);
         IMFEAT_MARK(3)

@@ -21,6 +21,7 @@ namespace imfeat {
 constexpr int kK2Vec = 2;      // 16-byte vectors per thread kept in registers (n <= 8192)
 
 struct K2Group {
+    uint32_t coarse[32];     // bit b of word s: some pixel has a value in [64*(32*s+b), +64)
     int vals[18];
     uint32_t wcnt[kGroupWarps];
     unsigned long long wpart[kGroupWarps];
@@ -28,7 +29,6 @@ struct K2Group {
 };
 struct K2Smem {
     uint32_t hist[32768];
-    uint32_t coarse[32];
     K2Group grp[2];
 };
 
@@ -36,9 +36,37 @@ struct K2Smem {
 __device__ __forceinline__ uint32_t k2_add(K2Smem& S, uint32_t x) {
     const uint32_t sh = (x & 1u) << 4;
     const uint32_t old = atomicAdd(&S.hist[x >> 1], 1u << sh);
-    const uint32_t b = x >> 6, bit = 1u << (b & 31u);
-    if (!(*(volatile uint32_t*)&S.coarse[b >> 5] & bit)) atomicOr(&S.coarse[b >> 5], bit);
     return (old >> sh) & 0xffffu;
+}
+
+// Occupied-block bitmap, built before the table is acquired.  Each lane ORs the 2048-value
+// "superblocks" of its pixels; per superblock present in the warp one REDUX.OR merges the lanes'
+// 64-value block bits and lane 0 publishes them (one shared-memory atomic per warp and
+// superblock instead of one per pixel).
+template <bool MASKED>
+__device__ __forceinline__ void k2_mark(uint32_t* coarse, const uint4& v, const uint2& m, bool have) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t x[8];
+    bool ok[8];
+    uint32_t sb = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t mb = (k < 2 ? m.x : m.y) >> (16 * (k & 1));
+        x[2 * k] = w[k] & 0xffffu; x[2 * k + 1] = w[k] >> 16;
+        ok[2 * k] = have && (!MASKED || (mb & 0xffu)); ok[2 * k + 1] = have && (!MASKED || (mb & 0xff00u));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (ok[k]) sb |= 1u << (x[k] >> 11);
+    uint32_t wsb = __reduce_or_sync(0xffffffffu, sb);
+    while (wsb) {
+        const uint32_t s = __ffs(wsb) - 1;
+        wsb &= wsb - 1;
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (ok[k] && (x[k] >> 11) == s) bits |= 1u << ((x[k] >> 6) & 31u);
+        bits = __reduce_or_sync(0xffffffffu, bits);
+        if ((threadIdx.x & 31) == 0 && (coarse[s] & bits) != bits) atomicOr(&coarse[s], bits);
+    }
 }
 
 // PHASE 0: histogram build + entropy terms, 2: sparse clear.
@@ -97,9 +125,38 @@ __device__ __forceinline__ void k2_walk(K2Smem& S, const Params& P, const Tile& 
     }
 }
 
+template <bool MASKED>
+__device__ __forceinline__ void k2_mark_walk(uint32_t* coarse, const Tile& T, int gt, const uint4* vreg,
+                                             const uint2* mreg) {
+    const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
+    const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
+    const int nfull = T.n >> 3, rem = T.n & 7;
+    // all lanes of a warp must take part in the REDUX: iterate warp-uniformly
+    const int wbase = gt & ~31;
+#pragma unroll
+    for (int i = 0; i < kK2Vec; ++i)
+        if (wbase + i * kGroupThreads < nfull)
+            k2_mark<MASKED>(coarse, vreg[i], mreg[i], gt + i * kGroupThreads < nfull);
+    for (int base = wbase + kK2Vec * kGroupThreads; base < nfull; base += kGroupThreads) {
+        const int idx = base + (gt & 31);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        uint2 m = make_uint2(0u, 0u);
+        if (idx < nfull) { v = ld_reuse(px4 + idx); if (MASKED) m = __ldg(mk2 + idx); }
+        k2_mark<MASKED>(coarse, v, m, idx < nfull);
+    }
+    if (gt < rem) {
+        const int i = nfull * 8 + gt;
+        if (!MASKED || T.mk[i] != 0) {
+            const uint32_t b = (uint32_t)T.px[i] >> 6;
+            atomicOr(&coarse[b >> 5], 1u << (b & 31u));
+        }
+    }
+}
+
 // One warp: numpy percentile (method "linear") from the histogram; ranks are 0-based positions
 // in the sorted multiset.
-__device__ __forceinline__ void k2_percentiles(K2Smem& S, int* vals, const Params& P, int n, double* o) {
+__device__ __forceinline__ void k2_percentiles(K2Smem& S, const uint32_t* coarse, int* vals, const Params& P,
+                                               int n, double* o) {
     const int lane = threadIdx.x & 31;
     int lo[9], hi[9], maxrank = 0;
 #pragma unroll
@@ -112,7 +169,7 @@ __device__ __forceinline__ void k2_percentiles(K2Smem& S, int* vals, const Param
     int cum = 0;
     bool done = false;
     for (int cw = 0; cw < 32 && !done; ++cw) {
-        uint32_t bits = S.coarse[cw];
+        uint32_t bits = coarse[cw];
         while (bits) {
             const int b = __ffs(bits) - 1;
             bits &= bits - 1;
@@ -158,7 +215,7 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k2_order_entropy_kernel(c
     K2Group& G = S.grp[g];
 
     for (int k = tid; k < 32768; k += kPingPongThreads) S.hist[k] = 0u;
-    if (tid < 32) S.coarse[tid] = 0u;
+    if (gt < 32) G.coarse[gt] = 0u;
     if (gt == 0) G.constant = 0;
     __syncthreads();
     if (g == 1) table_release(1);                          // the table starts out free for group 0
@@ -190,6 +247,7 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k2_order_entropy_kernel(c
                     if (MASKED) mreg[i] = __ldg(mk2 + idx);
                 }
             }
+            k2_mark_walk<MASKED>(G.coarse, T, gt, vreg, mreg);   // table-free
         }
         table_acquire(g);                                  // ---- table owned by this group ----
         int n = 0;
@@ -207,10 +265,10 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k2_order_entropy_kernel(c
                 for (int w = 0; w < kGroupWarps; ++w) n += (int)G.wcnt[w];
             }
             if (n > 0 && (int)maxold + 1 == n) G.constant = 1;   // one value only: entropy is exactly 0
-            if (gw == 0 && n > 0) k2_percentiles(S, G.vals, P, n, o);
+            if (gw == 0 && n > 0) k2_percentiles(S, G.coarse, G.vals, P, n, o);
             group_sync(g);                                 // percentile walk done
             k2_walk<2, MASKED>(S, P, T, gt, vreg, mreg, cnt, maxold, acc);
-            if (gt < 32) S.coarse[gt] = 0u;
+            if (gt < 32) G.coarse[gt] = 0u;
         }
         if (!(g == 1 && it == n_iter - 1)) table_release(g);   // ---- hand the table over ----
         if (active) {

@@ -15,8 +15,8 @@
 //   other group's table phase.
 // * contrast / dissimilarity / correlation come from exact integer sums over the pair stream,
 //   four pairs per SIMD video instruction (dp4a, vabsdiff4); ASM = sum_bins c^2 is accumulated
-//   from the atomics' return values (c^2 = sum_{k<c} (2k+1)), so there is no pass over the bins
-//   and no read-back pass.
+//   from the atomics' return values (c^2 = sum_{k<c} (2k+1) = 2*sum(old) + c), so there is no
+//   pass over the bins and no read-back pass.
 #pragma once
 #include "common.cuh"
 
@@ -119,21 +119,26 @@ __device__ __forceinline__ void k3_sums(const K3Smem& S, uint32_t I4, uint32_t J
         if ((vm >> (8 * b)) & 1u) A.hom += S.homtab[(D4 >> (8 * b)) & 0xffu];
 }
 
-// PHASE 0: bins += 1 (ASM from the returned old counts); PHASE 2: sparse clear.
+// PHASE 0: bins += 1, accumulating the returned old counts (sum_bins c^2 = 2*sum(old) + M);
+// PHASE 2: sparse clear.  Keys (i << 8 | j) are assembled two at a time with PRMT.
 template <int PHASE>
-__device__ __forceinline__ void k3_bins(K3Smem& S, uint32_t I4, uint32_t J4, uint32_t vm, uint32_t& sasm) {
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        if (!((vm >> (8 * b)) & 1u)) continue;
-        const uint32_t key = (((I4 >> (8 * b)) & 0xffu) << 8) | ((J4 >> (8 * b)) & 0xffu);
-        if (PHASE == 0) {
-            const uint32_t sh = (key & 1u) << 4;
-            const uint32_t old = (atomicAdd(&S.hist[key >> 1], 1u << sh) >> sh) & 0xffffu;
-            sasm += 2u * old + 1u;
-        } else {
-            S.hist[key >> 1] = 0u;
-        }
+__device__ __forceinline__ void k3_bin1(K3Smem& S, uint32_t key, uint32_t& sold) {
+    uint32_t* word = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(S.hist) + ((key << 1) & 0x1fffcu));
+    if (PHASE == 0) {
+        const uint32_t sh = (key & 1u) << 4;
+        sold += (atomicAdd(word, 1u << sh) >> sh) & 0xffffu;
+    } else {
+        *word = 0u;
     }
+}
+template <int PHASE>
+__device__ __forceinline__ void k3_bins(K3Smem& S, uint32_t I4, uint32_t J4, uint32_t vm, uint32_t& sold) {
+    const uint32_t K01 = __byte_perm(J4, I4, 0x5140);   // [j0, i0, j1, i1]
+    const uint32_t K23 = __byte_perm(J4, I4, 0x7362);   // [j2, i2, j3, i3]
+    if (vm & 0x00000001u) k3_bin1<PHASE>(S, K01 & 0xffffu, sold);
+    if (vm & 0x00000100u) k3_bin1<PHASE>(S, K01 >> 16, sold);
+    if (vm & 0x00010000u) k3_bin1<PHASE>(S, K23 & 0xffffu, sold);
+    if (vm & 0x01000000u) k3_bin1<PHASE>(S, K23 >> 16, sold);
 }
 
 template <bool MASKED, bool DUMP>
@@ -208,8 +213,8 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k3_glcm_kernel(const __gr
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     // pixels outside the mask may exceed vmax; they never enter a pair, clamp them
-                    const uint32_t a = min(k3_quant(w4[k] & 0xffffu, mul, sh), 255u);
-                    const uint32_t b = min(k3_quant(w4[k] >> 16, mul, sh), 255u);
+                    uint32_t a = k3_quant(w4[k] & 0xffffu, mul, sh), b = k3_quant(w4[k] >> 16, mul, sh);
+                    if (MASKED) { a = min(a, 255u); b = min(b, 255u); }
                     q[k >> 1] |= (a | (b << 8)) << (16 * (k & 1));
                 }
                 Gp.q8[2 * idx] = q[0];
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k3_glcm_kernel(const __gr
                             const long long vi = M * (long long)s[2] - (long long)s[0] * (long long)s[0];
                             const long long vj = M * (long long)s[3] - (long long)s[1] * (long long)s[1];
                             const long long cov = M * (long long)s[4] - (long long)s[0] * (long long)s[1];
-                            const double asmv = (double)s[6] / (Md * Md);
+                            const double asmv = (double)(2ull * s[6] + (unsigned long long)M) / (Md * Md);
                             o[0] = (double)con / Md;
                             o[1] = (double)s[5] / Md;
                             o[2] = homt / Md;

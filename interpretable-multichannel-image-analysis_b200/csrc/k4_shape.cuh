@@ -5,8 +5,13 @@
 //   shape   : area, perimeter (skimage.measure.perimeter, 4-neighbourhood: border = mask minus
 //             its 4-connected erosion, classified by the weighted 3x3 border sum), bounding box,
 //             extent, centroid, axis lengths and eccentricity of the inertia tensor, circularity.
-//             Every input of those formulas is an exact integer sum.
 //   moments : weighted centroid and the normalised central moments nu_pq, 2 <= p+q <= 3.
+//
+// Fast path (h, w <= 256): rows are bit-packed with __ballot_sync; erosion, border and the
+// perimeter classes are evaluated 32 pixels per bitwise instruction (bit-sliced adders), and
+// every sum -- including the raw intensity moments up to order 3 -- is an exact integer, turned
+// into central moments with 128-bit arithmetic in the epilogue.  Extreme aspect ratios fall back
+// to a simple per-pixel path.
 #pragma once
 #include "common.cuh"
 
@@ -14,164 +19,319 @@ namespace imfeat {
 
 constexpr int kK4Threads = 256;
 constexpr int kK4Warps = kK4Threads / 32;
+constexpr int kK4FastDim = 256;
+constexpr int kK4FastWords = kK4FastDim * (kK4FastDim / 32);
+constexpr int kK4NInt = 22;   // integer partials per warp
 
 struct K4Smem {
-    uint8_t m8[kMaxPixels + 16];
-    uint8_t b8[kMaxPixels + 16];
-    unsigned long long wint[kK4Warps][12];
+    unsigned long long wint[kK4Warps][kK4NInt];
     int wbox[kK4Warps][4];
     double wdbl[kK4Warps][7];
-    double centroid[2];
+    union {
+        struct { uint32_t mrow[kK4FastWords]; uint32_t brow[kK4FastWords]; } fast;
+        struct { uint8_t m8[kMaxPixels + 16]; uint8_t b8[kMaxPixels + 16]; } slow;
+    } u;
 };
+
+// exact warp sum of 64-bit integers with three 21-bit limbs (REDUX.ADD is one instruction)
+__device__ __forceinline__ unsigned long long warp_sum_redux(unsigned long long v) {
+    const uint32_t l0 = (uint32_t)v & 0x1fffffu, l1 = (uint32_t)(v >> 21) & 0x1fffffu;
+    const uint32_t l2 = (uint32_t)(v >> 42);
+    const unsigned long long s0 = __reduce_add_sync(0xffffffffu, l0);
+    const unsigned long long s1 = __reduce_add_sync(0xffffffffu, l1);
+    const unsigned long long s2 = __reduce_add_sync(0xffffffffu, l2);
+    return s0 + (s1 << 21) + (s2 << 42);
+}
+
+__device__ __forceinline__ double i128_to_double(__int128 v) {
+    const bool neg = v < 0;
+    const unsigned __int128 a = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
+    const double d = __ull2double_rn((unsigned long long)(a >> 64)) * 18446744073709551616.0 +
+                     __ull2double_rn((unsigned long long)a);
+    return neg ? -d : d;
+}
+
+// s: 0 area, 1 sr, 2 sc, 3 srr, 4 scc, 5 src, 6 n1, 7 n2, 8 n3
+__device__ __forceinline__ void k4_shape_epilogue(const Params& P, const Tile& T,
+                                                  const unsigned long long* s, int rmin, int rmax,
+                                                  int cmin, int cmax) {
+    double* o = T.out_row + P.col_shape + kNShape * T.slot;
+    const double SQ2 = 1.4142135623730951;
+    const double perim = (double)s[6] + (double)s[7] * SQ2 + (double)s[8] * ((1.0 + SQ2) / 2.0);
+    o[0] = (double)s[0];
+    o[1] = perim;
+    if (s[0] == 0) {
+        for (int k = 2; k < kNShape; ++k) o[k] = qnan();
+        if (T.status) atomicOr(T.status, kStEmptyMask);
+        return;
+    }
+    const long long A = (long long)s[0];
+    const double Ad = (double)A, A2 = Ad * Ad;
+    const double bbox = (double)(rmax - rmin + 1) * (double)(cmax - cmin + 1);
+    const long long an = A * (long long)s[4] - (long long)s[2] * (long long)s[2];
+    const long long cn = A * (long long)s[3] - (long long)s[1] * (long long)s[1];
+    const long long bn = A * (long long)s[5] - (long long)s[1] * (long long)s[2];
+    const double ia = (double)an / A2, ic = (double)cn / A2, ib = -(double)bn / A2;
+    const double hd = (double)(an - cn) / A2 * 0.5;
+    const double D = sqrt(__dadd_rn(__dmul_rn(hd, hd), __dmul_rn(ib, ib)));
+    const double l1 = __dadd_rn(__dmul_rn(__dadd_rn(ia, ic), 0.5), D);
+    double l2 = 0.0, ecc = 0.0;
+    if (l1 > 0) {
+        l2 = __ddiv_rn(__dsub_rn(__dmul_rn(ia, ic), __dmul_rn(ib, ib)), l1);
+        if (l2 < 0) l2 = 0;
+        ecc = __ddiv_rn(__dmul_rn(2.0, D), l1);
+        ecc = sqrt(fmin(fmax(ecc, 0.0), 1.0));
+    }
+    o[2] = bbox;
+    o[3] = Ad / bbox;
+    o[4] = (double)s[1] / Ad;
+    o[5] = (double)s[2] / Ad;
+    o[6] = 4.0 * sqrt(l1);
+    o[7] = 4.0 * sqrt(l2);
+    o[8] = ecc;
+    o[9] = perim > 0 ? 4.0 * 3.14159265358979323846 * Ad / (perim * perim) : qnan();
+}
+
+// raw moments m[0..9] = M00 M10 M01 M20 M11 M02 M30 M21 M12 M03 (exact integers, r,c <= 255)
+__device__ __forceinline__ void k4_moment_epilogue(const Params& P, const Tile& T, const unsigned long long* m) {
+    double* o = T.out_row + P.col_moment + kNMoment * T.slot;
+    if (m[0] == 0) {
+        for (int k = 0; k < kNMoment; ++k) o[k] = qnan();
+        return;
+    }
+    typedef __int128 i128;
+    const i128 M00 = m[0], M10 = m[1], M01 = m[2], M20 = m[3], M11 = m[4], M02 = m[5];
+    const i128 M30 = m[6], M21 = m[7], M12 = m[8], M03 = m[9];
+    const double M = (double)m[0];
+    // mu_pq * M00^(p+q-1), exactly
+    const double e20 = i128_to_double(M20 * M00 - M10 * M10);
+    const double e11 = i128_to_double(M11 * M00 - M10 * M01);
+    const double e02 = i128_to_double(M02 * M00 - M01 * M01);
+    const double e30 = i128_to_double(M30 * M00 * M00 - 3 * M10 * M20 * M00 + 2 * M10 * M10 * M10);
+    const double e21 = i128_to_double(M21 * M00 * M00 - 2 * M10 * M11 * M00 - M01 * M20 * M00 + 2 * M10 * M10 * M01);
+    const double e12 = i128_to_double(M12 * M00 * M00 - 2 * M01 * M11 * M00 - M10 * M02 * M00 + 2 * M01 * M01 * M10);
+    const double e03 = i128_to_double(M03 * M00 * M00 - 3 * M01 * M02 * M00 + 2 * M01 * M01 * M01);
+    const double M3 = M * M * M, M45 = M * M * pow(M, 2.5);   // M00^3, M00^4.5
+    o[0] = (double)m[1] / M;
+    o[1] = (double)m[2] / M;
+    o[2] = e20 / M3; o[3] = e11 / M3; o[4] = e02 / M3;
+    o[5] = e30 / M45; o[6] = e21 / M45; o[7] = e12 / M45; o[8] = e03 / M45;
+}
 
 template <bool MASKED>
 __global__ void __launch_bounds__(kK4Threads) k4_shape_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) unsigned char k4_smem_raw[];
     K4Smem& S = *reinterpret_cast<K4Smem*>(k4_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool want_mom = P.col_moment >= 0;
 
     for (long long t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
         const Tile T = resolve_tile(P, t);
         const int h = T.h, w = T.w, n = T.n;
-        // ---- 1. mask bytes (0/1) into shared memory ----
-        for (int i = tid; i < n; i += kK4Threads) S.m8[i] = MASKED ? (T.mk[i] != 0) : 1;
-        __syncthreads();
-        // ---- 2. border image ----
-        for (int i = tid; i < n; i += kK4Threads) {
-            const int r = i / w, c = i - r * w;
-            uint8_t b = 0;
-            if (S.m8[i]) {
-                const bool up = r > 0 && S.m8[i - w], dn = r + 1 < h && S.m8[i + w];
-                const bool lf = c > 0 && S.m8[i - 1], rt = c + 1 < w && S.m8[i + 1];
-                b = !(up && dn && lf && rt);
-            }
-            S.b8[i] = b;
-        }
-        __syncthreads();
-        // ---- 3. integer sums ----
-        unsigned long long a[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        // a: 0 area, 1 sr, 2 sc, 3 srr, 4 scc, 5 src, 6 n1, 7 n2, 8 n3, 9 M00, 10 M10, 11 M01
+        unsigned long long a[kK4NInt];
+#pragma unroll
+        for (int k = 0; k < kK4NInt; ++k) a[k] = 0ull;
+        // a: 0 area 1 sr 2 sc 3 srr 4 scc 5 src 6 n1 7 n2 8 n3 | 9.. raw moments M00 M10 M01 M20 M11
+        //    M02 M30 M21 M12 M03 (fast path) or M00 M10 M01 (slow path)
         int rmin = 1 << 30, rmax = -1, cmin = 1 << 30, cmax = -1;
-        for (int i = tid; i < n; i += kK4Threads) {
-            if (!S.m8[i]) continue;
-            const int r = i / w, c = i - r * w;
-            a[0] += 1; a[1] += r; a[2] += c;
-            a[3] += (unsigned long long)r * r; a[4] += (unsigned long long)c * c;
-            a[5] += (unsigned long long)r * c;
-            rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
-            if (S.b8[i]) {
-                int v = 1;
-#pragma unroll
-                for (int dr = -1; dr <= 1; ++dr)
-#pragma unroll
-                    for (int dc = -1; dc <= 1; ++dc) {
-                        if (dr == 0 && dc == 0) continue;
-                        const int rr = r + dr, cc = c + dc;
-                        if (rr < 0 || rr >= h || cc < 0 || cc >= w) continue;
-                        if (S.b8[rr * w + cc]) v += (dr != 0 && dc != 0) ? 10 : 2;
+        const bool fast = h <= kK4FastDim && w <= kK4FastDim;
+
+        if (fast) {
+            const int Pw = (w + 31) >> 5;                  // mask words per row
+            uint32_t area = 0, sr = 0, sc = 0, srr = 0, scc = 0, src = 0, m00 = 0;
+            unsigned long long m10 = 0, m01 = 0, m20 = 0, m11 = 0, m02 = 0, m30 = 0, m21 = 0, m12 = 0, m03 = 0;
+            // ---- pass A: one warp per row, lanes over columns ----
+            for (int r = warp; r < h; r += kK4Warps) {
+                const uint32_t r1 = r, r2 = r * r, r3 = r2 * r;
+                for (int c0 = 0; c0 < w; c0 += 32) {
+                    const int c = c0 + lane;
+                    const int i = r * w + c;
+                    const bool m = c < w && (!MASKED || T.mk[i] != 0);
+                    const uint32_t bal = __ballot_sync(0xffffffffu, m);
+                    if (lane == 0) S.u.fast.mrow[r * Pw + (c0 >> 5)] = bal;
+                    if (m) {
+                        area += 1; sr += r1; srr += r2; sc += c; scc += c * c; src += r1 * c;
+                        rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
+                        if (want_mom) {
+                            const uint32_t v0 = T.px[i];
+                            const uint32_t v1 = v0 * (uint32_t)c, v2 = v1 * (uint32_t)c;
+                            const unsigned long long v3 = (unsigned long long)v2 * (uint32_t)c;
+                            m00 += v0;
+                            m10 += (unsigned long long)v0 * r1; m20 += (unsigned long long)v0 * r2;
+                            m30 += (unsigned long long)v0 * r3;
+                            m01 += v1; m11 += (unsigned long long)v1 * r1; m21 += (unsigned long long)v1 * r2;
+                            m02 += v2; m12 += (unsigned long long)v2 * r1;
+                            m03 += v3;
+                        }
                     }
-                const unsigned long long C1 = (1ull << 5) | (1ull << 7) | (1ull << 15) | (1ull << 17) |
-                                              (1ull << 25) | (1ull << 27);
-                const unsigned long long C2 = (1ull << 21) | (1ull << 33);
-                const unsigned long long C3 = (1ull << 13) | (1ull << 23);
-                a[6] += (C1 >> v) & 1ull; a[7] += (C2 >> v) & 1ull; a[8] += (C3 >> v) & 1ull;
+                }
             }
-            if (P.col_moment >= 0) {
-                const unsigned long long x = T.px[i];
-                a[9] += x; a[10] += x * r; a[11] += x * c;
+            a[0] = __reduce_add_sync(0xffffffffu, area); a[1] = __reduce_add_sync(0xffffffffu, sr);
+            a[2] = __reduce_add_sync(0xffffffffu, sc);   a[3] = __reduce_add_sync(0xffffffffu, srr);
+            a[4] = __reduce_add_sync(0xffffffffu, scc);  a[5] = __reduce_add_sync(0xffffffffu, src);
+            if (want_mom) {
+                a[9] = __reduce_add_sync(0xffffffffu, m00);
+                a[10] = warp_sum_redux(m10); a[11] = warp_sum_redux(m01); a[12] = warp_sum_redux(m20);
+                a[13] = warp_sum_redux(m11); a[14] = warp_sum_redux(m02); a[15] = warp_sum_redux(m30);
+                a[16] = warp_sum_redux(m21); a[17] = warp_sum_redux(m12); a[18] = warp_sum_redux(m03);
             }
-        }
+            __syncthreads();                               // mask rows complete
+            // ---- pass B: border = mask & ~erosion4(mask), 32 pixels per word ----
+            const int words = h * Pw;
+            for (int idx = tid; idx < words; idx += kK4Threads) {
+                const int r = idx / Pw, cw = idx - r * Pw;
+                const uint32_t* M = S.u.fast.mrow;
+                const uint32_t m = M[idx];
+                const uint32_t up = r > 0 ? M[idx - Pw] : 0u, dn = r + 1 < h ? M[idx + Pw] : 0u;
+                const uint32_t ml = cw > 0 ? M[idx - 1] : 0u, mr = cw + 1 < Pw ? M[idx + 1] : 0u;
+                const uint32_t L = (m << 1) | (ml >> 31), R = (m >> 1) | (mr << 31);
+                S.u.fast.brow[idx] = m & ~(up & dn & L & R);
+            }
+            __syncthreads();
+            // ---- pass C: classify border pixels by their 3x3 border neighbourhood ----
+            uint32_t n1 = 0, n2 = 0, n3 = 0;
+            for (int idx = tid; idx < words; idx += kK4Threads) {
+                const uint32_t* B = S.u.fast.brow;
+                const uint32_t b = B[idx];
+                if (!b) continue;
+                const int r = idx / Pw, cw = idx - r * Pw;
+                const bool hu = r > 0, hd = r + 1 < h, hl = cw > 0, hr = cw + 1 < Pw;
+                const uint32_t bl = hl ? B[idx - 1] : 0u, br = hr ? B[idx + 1] : 0u;
+                const uint32_t u = hu ? B[idx - Pw] : 0u, ul = (hu && hl) ? B[idx - Pw - 1] : 0u;
+                const uint32_t ur = (hu && hr) ? B[idx - Pw + 1] : 0u;
+                const uint32_t d = hd ? B[idx + Pw] : 0u, dl = (hd && hl) ? B[idx + Pw - 1] : 0u;
+                const uint32_t dr = (hd && hr) ? B[idx + Pw + 1] : 0u;
+                const uint32_t N = u, Sd = d, W = (b << 1) | (bl >> 31), E = (b >> 1) | (br << 31);
+                const uint32_t NW = (u << 1) | (ul >> 31), NE = (u >> 1) | (ur << 31);
+                const uint32_t SW = (d << 1) | (dl >> 31), SE = (d >> 1) | (dr << 31);
+                // bit-sliced sums o = N+S+W+E, dd = NW+NE+SW+SE (0..4 each)
+                uint32_t s1 = N ^ Sd ^ W, c1 = (N & Sd) | (N & W) | (Sd & W);
+                const uint32_t o0 = s1 ^ E, c2 = s1 & E, o1 = c1 ^ c2, o2 = c1 & c2;
+                s1 = NW ^ NE ^ SW; c1 = (NW & NE) | (NW & SW) | (NE & SW);
+                const uint32_t d0 = s1 ^ SE, c3 = s1 & SE, d1 = c1 ^ c3, d2 = c1 & c3;
+                const uint32_t o_is0 = ~o0 & ~o1 & ~o2, o_is1 = o0 & ~o1 & ~o2, o_23 = o1 & ~o2;
+                const uint32_t d_is1 = d0 & ~d1 & ~d2, d_is2 = ~d0 & d1 & ~d2, d_is3 = d0 & d1 & ~d2;
+                const uint32_t d_le2 = ~d2 & ~(d1 & d0);
+                n1 += __popc(b & o_23 & d_le2);                        // weights {5,7,15,17,25,27}
+                n2 += __popc(b & ((o_is0 & d_is2) | (o_is1 & d_is3))); // {21,33}
+                n3 += __popc(b & o_is1 & (d_is1 | d_is2));             // {13,23}
+            }
+            a[6] = __reduce_add_sync(0xffffffffu, n1);
+            a[7] = __reduce_add_sync(0xffffffffu, n2);
+            a[8] = __reduce_add_sync(0xffffffffu, n3);
+        } else {
+            // ---- generic per-pixel path (very wide / very tall tiles) ----
+            for (int i = tid; i < n; i += kK4Threads) S.u.slow.m8[i] = MASKED ? (T.mk[i] != 0) : 1;
+            __syncthreads();
+            for (int i = tid; i < n; i += kK4Threads) {
+                const int r = i / w, c = i - r * w;
+                uint8_t b = 0;
+                if (S.u.slow.m8[i]) {
+                    const bool up = r > 0 && S.u.slow.m8[i - w], dn = r + 1 < h && S.u.slow.m8[i + w];
+                    const bool lf = c > 0 && S.u.slow.m8[i - 1], rt = c + 1 < w && S.u.slow.m8[i + 1];
+                    b = !(up && dn && lf && rt);
+                }
+                S.u.slow.b8[i] = b;
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += kK4Threads) {
+                if (!S.u.slow.m8[i]) continue;
+                const int r = i / w, c = i - r * w;
+                a[0] += 1; a[1] += r; a[2] += c;
+                a[3] += (unsigned long long)r * r; a[4] += (unsigned long long)c * c;
+                a[5] += (unsigned long long)r * c;
+                rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
+                if (S.u.slow.b8[i]) {
+                    int v = 1;
 #pragma unroll
-        for (int k = 0; k < 12; ++k) a[k] = warp_sum(a[k]);
+                    for (int dr = -1; dr <= 1; ++dr)
+#pragma unroll
+                        for (int dc = -1; dc <= 1; ++dc) {
+                            if (dr == 0 && dc == 0) continue;
+                            const int rr = r + dr, cc = c + dc;
+                            if (rr < 0 || rr >= h || cc < 0 || cc >= w) continue;
+                            if (S.u.slow.b8[rr * w + cc]) v += (dr != 0 && dc != 0) ? 10 : 2;
+                        }
+                    const unsigned long long C1 = (1ull << 5) | (1ull << 7) | (1ull << 15) | (1ull << 17) |
+                                                  (1ull << 25) | (1ull << 27);
+                    const unsigned long long C2 = (1ull << 21) | (1ull << 33);
+                    const unsigned long long C3 = (1ull << 13) | (1ull << 23);
+                    a[6] += (C1 >> v) & 1ull; a[7] += (C2 >> v) & 1ull; a[8] += (C3 >> v) & 1ull;
+                }
+                if (want_mom) {
+                    const unsigned long long x = T.px[i];
+                    a[9] += x; a[10] += x * r; a[11] += x * c;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 12; ++k) a[k] = warp_sum(a[k]);
+        }
         rmin = __reduce_min_sync(0xffffffffu, rmin); rmax = __reduce_max_sync(0xffffffffu, rmax);
         cmin = __reduce_min_sync(0xffffffffu, cmin); cmax = __reduce_max_sync(0xffffffffu, cmax);
         if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 12; ++k) S.wint[warp][k] = a[k];
+            for (int k = 0; k < kK4NInt; ++k) S.wint[warp][k] = a[k];
             S.wbox[warp][0] = rmin; S.wbox[warp][1] = rmax; S.wbox[warp][2] = cmin; S.wbox[warp][3] = cmax;
         }
         __syncthreads();
-        unsigned long long s[12];
+        unsigned long long s[kK4NInt];
+        if (warp == 0 || !fast) {
 #pragma unroll
-        for (int k = 0; k < 12; ++k) {
-            s[k] = 0;
-            for (int wv = 0; wv < kK4Warps; ++wv) s[k] += S.wint[wv][k];
-        }
-        for (int wv = 0; wv < kK4Warps; ++wv) {
-            rmin = min(rmin, S.wbox[wv][0]); rmax = max(rmax, S.wbox[wv][1]);
-            cmin = min(cmin, S.wbox[wv][2]); cmax = max(cmax, S.wbox[wv][3]);
-        }
-        // ---- 4. shape epilogue ----
-        if (tid == 0 && P.col_shape >= 0) {
-            double* o = T.out_row + P.col_shape + kNShape * T.slot;
-            const double SQ2 = 1.4142135623730951;
-            const double perim = (double)s[6] + (double)s[7] * SQ2 + (double)s[8] * ((1.0 + SQ2) / 2.0);
-            o[0] = (double)s[0];
-            o[1] = perim;
-            if (s[0] == 0) {
-                for (int k = 2; k < kNShape; ++k) o[k] = qnan();
-                if (T.status) atomicOr(T.status, kStEmptyMask);
-            } else {
-                const long long A = (long long)s[0];
-                const double Ad = (double)A, A2 = Ad * Ad;
-                const double bbox = (double)(rmax - rmin + 1) * (double)(cmax - cmin + 1);
-                const long long an = A * (long long)s[4] - (long long)s[2] * (long long)s[2];
-                const long long cn = A * (long long)s[3] - (long long)s[1] * (long long)s[1];
-                const long long bn = A * (long long)s[5] - (long long)s[1] * (long long)s[2];
-                const double ia = (double)an / A2, ic = (double)cn / A2, ib = -(double)bn / A2;
-                const double hd = (double)(an - cn) / A2 * 0.5;
-                const double D = sqrt(__dadd_rn(__dmul_rn(hd, hd), __dmul_rn(ib, ib)));
-                const double l1 = __dadd_rn(__dmul_rn(__dadd_rn(ia, ic), 0.5), D);
-                double l2 = 0.0, ecc = 0.0;
-                if (l1 > 0) {
-                    l2 = __ddiv_rn(__dsub_rn(__dmul_rn(ia, ic), __dmul_rn(ib, ib)), l1);
-                    if (l2 < 0) l2 = 0;
-                    ecc = __ddiv_rn(__dmul_rn(2.0, D), l1);
-                    ecc = sqrt(fmin(fmax(ecc, 0.0), 1.0));
-                }
-                o[2] = bbox;
-                o[3] = Ad / bbox;
-                o[4] = (double)s[1] / Ad;
-                o[5] = (double)s[2] / Ad;
-                o[6] = 4.0 * sqrt(l1);
-                o[7] = 4.0 * sqrt(l2);
-                o[8] = ecc;
-                o[9] = perim > 0 ? 4.0 * 3.14159265358979323846 * Ad / (perim * perim) : qnan();
+            for (int k = 0; k < kK4NInt; ++k) {
+                s[k] = 0;
+                for (int wv = 0; wv < kK4Warps; ++wv) s[k] += S.wint[wv][k];
+            }
+            for (int wv = 0; wv < kK4Warps; ++wv) {
+                rmin = min(rmin, S.wbox[wv][0]); rmax = max(rmax, S.wbox[wv][1]);
+                cmin = min(cmin, S.wbox[wv][2]); cmax = max(cmax, S.wbox[wv][3]);
             }
         }
-        // ---- 5. spatial moments (second pass around the exact weighted centroid) ----
-        if (P.col_moment >= 0) {
-            double* o = T.out_row + P.col_moment + kNMoment * T.slot;
-            if (s[9] == 0) {
-                if (tid == 0) for (int k = 0; k < kNMoment; ++k) o[k] = qnan();
-            } else {
-                const double M = (double)s[9];
-                const double cr = (double)s[10] / M, cc = (double)s[11] / M;
-                double mu[7] = {0, 0, 0, 0, 0, 0, 0};   // 20 11 02 30 21 12 03
-                for (int i = tid; i < n; i += kK4Threads) {
-                    if (!S.m8[i]) continue;
-                    const int r = i / w, c = i - r * w;
-                    const double x = (double)T.px[i], dr = (double)r - cr, dc = (double)c - cc;
-                    const double rr = dr * dr, cc2 = dc * dc;
-                    mu[0] += rr * x; mu[1] += dr * dc * x; mu[2] += cc2 * x;
-                    mu[3] += rr * dr * x; mu[4] += rr * dc * x; mu[5] += dr * cc2 * x; mu[6] += cc2 * dc * x;
-                }
-#pragma unroll
-                for (int k = 0; k < 7; ++k) mu[k] = warp_sum(mu[k]);
-                if (lane == 0)
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) S.wdbl[warp][k] = mu[k];
-                __syncthreads();
-                if (tid == 0) {
-                    double tot[7];
-                    for (int k = 0; k < 7; ++k) {
-                        tot[k] = 0.0;
-                        for (int wv = 0; wv < kK4Warps; ++wv) tot[k] += S.wdbl[wv][k];
+        if (tid == 0 && P.col_shape >= 0) k4_shape_epilogue(P, T, s, rmin, rmax, cmin, cmax);
+        if (want_mom) {
+            if (fast) {
+                if (tid == 32 % kK4Threads) {
+                    // second warp's lane 0 re-sums (keeps the two epilogues on different warps)
+                    unsigned long long mm[10];
+                    for (int k = 0; k < 10; ++k) {
+                        mm[k] = 0;
+                        for (int wv = 0; wv < kK4Warps; ++wv) mm[k] += S.wint[wv][9 + k];
                     }
-                    const double n2 = M * M, n3 = pow(M, 2.5);
-                    o[0] = cr; o[1] = cc;
-                    o[2] = tot[0] / n2; o[3] = tot[1] / n2; o[4] = tot[2] / n2;
-                    o[5] = tot[3] / n3; o[6] = tot[4] / n3; o[7] = tot[5] / n3; o[8] = tot[6] / n3;
+                    k4_moment_epilogue(P, T, mm);
+                }
+            } else {
+                // slow path: second pass around the weighted centroid in double precision
+                double* o = T.out_row + P.col_moment + kNMoment * T.slot;
+                if (s[9] == 0) {
+                    if (tid == 0) for (int k = 0; k < kNMoment; ++k) o[k] = qnan();
+                } else {
+                    const double M = (double)s[9];
+                    const double cr = (double)s[10] / M, cc = (double)s[11] / M;
+                    double mu[7] = {0, 0, 0, 0, 0, 0, 0};   // 20 11 02 30 21 12 03
+                    for (int i = tid; i < n; i += kK4Threads) {
+                        if (!S.u.slow.m8[i]) continue;
+                        const int r = i / w, c = i - r * w;
+                        const double x = (double)T.px[i], dr = (double)r - cr, dc = (double)c - cc;
+                        const double rr = dr * dr, cc2 = dc * dc;
+                        mu[0] += rr * x; mu[1] += dr * dc * x; mu[2] += cc2 * x;
+                        mu[3] += rr * dr * x; mu[4] += rr * dc * x; mu[5] += dr * cc2 * x; mu[6] += cc2 * dc * x;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) mu[k] = warp_sum(mu[k]);
+                    if (lane == 0)
+#pragma unroll
+                        for (int k = 0; k < 7; ++k) S.wdbl[warp][k] = mu[k];
+                    __syncthreads();
+                    if (tid == 0) {
+                        double tot[7];
+                        for (int k = 0; k < 7; ++k) {
+                            tot[k] = 0.0;
+                            for (int wv = 0; wv < kK4Warps; ++wv) tot[k] += S.wdbl[wv][k];
+                        }
+                        const double n2 = M * M, n3 = pow(M, 2.5);
+                        o[0] = cr; o[1] = cc;
+                        o[2] = tot[0] / n2; o[3] = tot[1] / n2; o[4] = tot[2] / n2;
+                        o[5] = tot[3] / n3; o[6] = tot[4] / n3; o[7] = tot[5] / n3; o[8] = tot[6] / n3;
+                    }
                 }
             }
         }
