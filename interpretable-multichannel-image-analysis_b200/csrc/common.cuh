@@ -48,12 +48,11 @@ struct Tile {
     int slot, h, w, n;
 };
 
-__device__ __forceinline__ Tile resolve_tile(const Params& P, long long t) {
+__device__ __forceinline__ Tile resolve_tile_rs(const Params& P, uint32_t row32, uint32_t slot32) {
     Tile T;
-    // n_tiles < 2^31 is enforced by the host API: 32-bit division is much cheaper than 64-bit
-    const uint32_t row32 = (uint32_t)t / (uint32_t)P.c_out;
     const long long row = row32;
-    const int slot = (int)((uint32_t)t - row32 * (uint32_t)P.c_out);
+    const int slot = (int)slot32;
+    const long long t = row * P.c_out + slot;
     const long long so = P.src_obj ? (long long)P.src_obj[t] : row;
     const int ch = P.chan ? P.chan[slot] : slot;
     T.h = P.sizes ? P.sizes[2 * so] : P.hs;
@@ -67,6 +66,28 @@ __device__ __forceinline__ Tile resolve_tile(const Params& P, long long t) {
     T.slot = slot;
     return T;
 }
+
+__device__ __forceinline__ Tile resolve_tile(const Params& P, long long t) {
+    // n_tiles < 2^31 is enforced by the host API: 32-bit division is much cheaper than 64-bit
+    const uint32_t row32 = (uint32_t)t / (uint32_t)P.c_out;
+    return resolve_tile_rs(P, row32, (uint32_t)t - row32 * (uint32_t)P.c_out);
+}
+
+// Walks tiles t0, t0 + stride, t0 + 2*stride, ... keeping (row, slot) = (t / c_out, t % c_out)
+// incrementally, so the per-tile integer divisions disappear from the persistent loops.
+struct TileWalk {
+    uint32_t row, slot, drow, dslot, c_out;
+    __device__ __forceinline__ void init(const Params& P, long long t0, long long stride) {
+        c_out = (uint32_t)P.c_out;
+        row = (uint32_t)t0 / c_out; slot = (uint32_t)t0 - row * c_out;
+        drow = (uint32_t)stride / c_out; dslot = (uint32_t)stride - drow * c_out;
+    }
+    __device__ __forceinline__ void next() {
+        row += drow; slot += dslot;
+        if (slot >= c_out) { slot -= c_out; ++row; }
+    }
+    __device__ __forceinline__ long long tile() const { return (long long)row * c_out + slot; }
+};
 
 // 128-bit streaming load: the tile is read once per kernel, keep it out of L1.
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
@@ -110,6 +131,16 @@ constexpr int kPingPongThreads = 2 * kGroupThreads;
 __device__ __forceinline__ void group_sync(int g) { bar_sync(1 + g, kGroupThreads); }
 __device__ __forceinline__ void table_acquire(int g) { bar_sync(3 + g, kPingPongThreads); }
 __device__ __forceinline__ void table_release(int g) { bar_arrive(3 + (g ^ 1), kPingPongThreads); }
+
+// exact warp sum of 64-bit integers with three 21-bit limbs (REDUX.ADD is one instruction)
+__device__ __forceinline__ unsigned long long warp_sum_redux(unsigned long long v) {
+    const uint32_t l0 = (uint32_t)v & 0x1fffffu, l1 = (uint32_t)(v >> 21) & 0x1fffffu;
+    const uint32_t l2 = (uint32_t)(v >> 42);
+    const unsigned long long s0 = __reduce_add_sync(0xffffffffu, l0);
+    const unsigned long long s1 = __reduce_add_sync(0xffffffffu, l1);
+    const unsigned long long s2 = __reduce_add_sync(0xffffffffu, l2);
+    return s0 + (s1 << 21) + (s2 << 42);
+}
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 

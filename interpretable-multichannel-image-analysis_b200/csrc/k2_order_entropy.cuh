@@ -39,33 +39,22 @@ __device__ __forceinline__ uint32_t k2_add(K2Smem& S, uint32_t x) {
     return (old >> sh) & 0xffffu;
 }
 
-// Occupied-block bitmap, built before the table is acquired.  Each lane ORs the 2048-value
-// "superblocks" of its pixels; per superblock present in the warp one REDUX.OR merges the lanes'
-// 64-value block bits and lane 0 publishes them (one shared-memory atomic per warp and
-// superblock instead of one per pixel).
+// Occupied-block bitmap, built before the table is acquired.  A superset is enough (an empty
+// marked block only costs the percentile walk one cheap step), so each warp marks the whole block
+// range [min >> 6, max >> 6] of its pixels: packed 16-bit min/max per lane, two REDUX per warp, and
+// lane 0 publishes the range -- instead of one shared-memory atomic per pixel.
 template <bool MASKED>
-__device__ __forceinline__ void k2_mark(uint32_t* coarse, const uint4& v, const uint2& m, bool have) {
+__device__ __forceinline__ void k2_range(const uint4& v, const uint2& m, uint32_t& mn2, uint32_t& mx2) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t x[8];
-    bool ok[8];
-    uint32_t sb = 0u;
+    if (MASKED) {
+        uint32_t h[4];
+        mask_halfwords(m.x, h[0], h[1]);
+        mask_halfwords(m.y, h[2], h[3]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t mb = (k < 2 ? m.x : m.y) >> (16 * (k & 1));
-        x[2 * k] = w[k] & 0xffffu; x[2 * k + 1] = w[k] >> 16;
-        ok[2 * k] = have && (!MASKED || (mb & 0xffu)); ok[2 * k + 1] = have && (!MASKED || (mb & 0xff00u));
-    }
+        for (int k = 0; k < 4; ++k) { mn2 = __vminu2(mn2, w[k] | ~h[k]); mx2 = __vmaxu2(mx2, w[k] & h[k]); }
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) if (ok[k]) sb |= 1u << (x[k] >> 11);
-    uint32_t wsb = __reduce_or_sync(0xffffffffu, sb);
-    while (wsb) {
-        const uint32_t s = __ffs(wsb) - 1;
-        wsb &= wsb - 1;
-        uint32_t bits = 0u;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (ok[k] && (x[k] >> 11) == s) bits |= 1u << ((x[k] >> 6) & 31u);
-        bits = __reduce_or_sync(0xffffffffu, bits);
-        if ((threadIdx.x & 31) == 0 && (coarse[s] & bits) != bits) atomicOr(&coarse[s], bits);
+        for (int k = 0; k < 4; ++k) { mn2 = __vminu2(mn2, w[k]); mx2 = __vmaxu2(mx2, w[k]); }
     }
 }
 
@@ -131,24 +120,40 @@ __device__ __forceinline__ void k2_mark_walk(uint32_t* coarse, const Tile& T, in
     const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
     const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
     const int nfull = T.n >> 3, rem = T.n & 7;
-    // all lanes of a warp must take part in the REDUX: iterate warp-uniformly
-    const int wbase = gt & ~31;
+    uint32_t mn2 = 0xffffffffu, mx2 = 0u;
+    bool any = !MASKED;
 #pragma unroll
     for (int i = 0; i < kK2Vec; ++i)
-        if (wbase + i * kGroupThreads < nfull)
-            k2_mark<MASKED>(coarse, vreg[i], mreg[i], gt + i * kGroupThreads < nfull);
-    for (int base = wbase + kK2Vec * kGroupThreads; base < nfull; base += kGroupThreads) {
-        const int idx = base + (gt & 31);
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (gt + i * kGroupThreads < nfull) {
+            k2_range<MASKED>(vreg[i], mreg[i], mn2, mx2);
+            if (MASKED) any |= (mreg[i].x | mreg[i].y) != 0u;
+        }
+    for (int idx = gt + kK2Vec * kGroupThreads; idx < nfull; idx += kGroupThreads) {
+        const uint4 v = ld_reuse(px4 + idx);
         uint2 m = make_uint2(0u, 0u);
-        if (idx < nfull) { v = ld_reuse(px4 + idx); if (MASKED) m = __ldg(mk2 + idx); }
-        k2_mark<MASKED>(coarse, v, m, idx < nfull);
+        if (MASKED) { m = __ldg(mk2 + idx); any |= (m.x | m.y) != 0u; }
+        k2_range<MASKED>(v, m, mn2, mx2);
     }
     if (gt < rem) {
         const int i = nfull * 8 + gt;
         if (!MASKED || T.mk[i] != 0) {
-            const uint32_t b = (uint32_t)T.px[i] >> 6;
-            atomicOr(&coarse[b >> 5], 1u << (b & 31u));
+            const uint32_t x = T.px[i];
+            mn2 = __vminu2(mn2, x | 0xffff0000u);
+            mx2 = __vmaxu2(mx2, x);
+            any = true;
+        }
+    }
+    const bool have = (gt < nfull || gt < rem) && any;      // this lane saw at least one valid pixel
+    uint32_t lo = have ? min(mn2 & 0xffffu, mn2 >> 16) : 0xffffu;
+    uint32_t hi = have ? max(mx2 & 0xffffu, mx2 >> 16) : 0u;
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((gt & 31) == 0 && lo <= hi) {
+        const uint32_t b0 = lo >> 6, b1 = hi >> 6;
+        for (uint32_t s = b0 >> 5; s <= (b1 >> 5); ++s) {
+            const uint32_t from = s == (b0 >> 5) ? (b0 & 31u) : 0u, to = s == (b1 >> 5) ? (b1 & 31u) : 31u;
+            const uint32_t bits = (0xffffffffu >> (31u - to)) & (0xffffffffu << from);
+            if ((coarse[s] & bits) != bits) atomicOr(&coarse[s], bits);
         }
     }
 }
@@ -223,7 +228,9 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k2_order_entropy_kernel(c
     const long long first = blockIdx.x;
     const long long mine = first < P.n_tiles ? (P.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
     const long long n_iter = (mine + 1) / 2;
-    for (long long it = 0; it < n_iter; ++it) {
+    TileWalk walk;
+    walk.init(P, first + (long long)g * gridDim.x < P.n_tiles ? first + (long long)g * gridDim.x : 0, 2ll * gridDim.x);
+    for (long long it = 0; it < n_iter; ++it, walk.next()) {
         const long long k = 2 * it + g;
         const bool active = k < mine;
         Tile T;
@@ -233,7 +240,7 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k2_order_entropy_kernel(c
         uint32_t cnt = 0, maxold = 0;
         unsigned long long acc = 0ull;
         if (active) {
-            T = resolve_tile(P, first + k * gridDim.x);
+            T = resolve_tile_rs(P, walk.row, walk.slot);
             o = T.out_row + P.col_basic + kNBasic * T.slot;
             const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
             const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
@@ -259,11 +266,7 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k2_order_entropy_kernel(c
             }
             group_sync(g);                                 // histogram complete
             n = T.n;
-            if (MASKED) {
-                n = 0;
-#pragma unroll
-                for (int w = 0; w < kGroupWarps; ++w) n += (int)G.wcnt[w];
-            }
+            if (MASKED) n = (int)__reduce_add_sync(0xffffffffu, lane < kGroupWarps ? G.wcnt[lane] : 0u);
             if (n > 0 && (int)maxold + 1 == n) G.constant = 1;   // one value only: entropy is exactly 0
             if (gw == 0 && n > 0) k2_percentiles(S, G.coarse, G.vals, P, n, o);
             group_sync(g);                                 // percentile walk done

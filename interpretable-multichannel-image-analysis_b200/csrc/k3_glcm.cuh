@@ -22,11 +22,10 @@
 
 namespace imfeat {
 
-constexpr int kK3Items = 2;    // pair groups per thread cached in registers (covers 64x64)
 
 struct K3Group {
-    double whom[kGroupWarps];
-    uint32_t wred[kGroupWarps][8];
+    unsigned long long homfix[kMaxAngles];     // sum 1/(1+d^2) in 2^-40 fixed point, per direction
+    uint32_t acc[kMaxAngles][8];               // si sj sii sjj sij sd sold m, per direction
     uint32_t wmax[kGroupWarps];
     uint32_t q8[kMaxPixels / 4 + 4];      // quantised pixels (bytes) + slack for unaligned reads
     uint32_t mbits[kMaxPixels / 32 + 2];  // one bit per pixel: inside the mask (masked variant)
@@ -114,9 +113,16 @@ __device__ __forceinline__ void k3_sums(const K3Smem& S, uint32_t I4, uint32_t J
     A.sd += __vsadu4(I4, J4);
     A.m += __popc(vm) >> 3;
     const uint32_t D4 = __vabsdiffu4(I4, J4);
+    if (vm == 0xffffffffu) {
+        A.hom += S.homtab[D4 & 0xffu];
+        A.hom += S.homtab[(D4 >> 8) & 0xffu];
+        A.hom += S.homtab[(D4 >> 16) & 0xffu];
+        A.hom += S.homtab[D4 >> 24];
+    } else {
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
-        if ((vm >> (8 * b)) & 1u) A.hom += S.homtab[(D4 >> (8 * b)) & 0xffu];
+        for (int b = 0; b < 4; ++b)
+            if ((vm >> (8 * b)) & 1u) A.hom += S.homtab[(D4 >> (8 * b)) & 0xffu];
+    }
 }
 
 // PHASE 0: bins += 1, accumulating the returned old counts (sum_bins c^2 = 2*sum(old) + M);
@@ -135,6 +141,13 @@ template <int PHASE>
 __device__ __forceinline__ void k3_bins(K3Smem& S, uint32_t I4, uint32_t J4, uint32_t vm, uint32_t& sold) {
     const uint32_t K01 = __byte_perm(J4, I4, 0x5140);   // [j0, i0, j1, i1]
     const uint32_t K23 = __byte_perm(J4, I4, 0x7362);   // [j2, i2, j3, i3]
+    if (vm == 0xffffffffu) {
+        k3_bin1<PHASE>(S, K01 & 0xffffu, sold);
+        k3_bin1<PHASE>(S, K01 >> 16, sold);
+        k3_bin1<PHASE>(S, K23 & 0xffffu, sold);
+        k3_bin1<PHASE>(S, K23 >> 16, sold);
+        return;
+    }
     if (vm & 0x00000001u) k3_bin1<PHASE>(S, K01 & 0xffffu, sold);
     if (vm & 0x00000100u) k3_bin1<PHASE>(S, K01 >> 16, sold);
     if (vm & 0x00010000u) k3_bin1<PHASE>(S, K23 & 0xffffu, sold);
@@ -151,20 +164,24 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k3_glcm_kernel(const __gr
 
     for (int k = tid; k < 32768; k += kPingPongThreads) S.hist[k] = 0u;
     if (tid < 256) S.homtab[tid] = 1.0 / (1.0 + (double)(tid * tid));
+    if (gt < kMaxAngles * 8) Gp.acc[gt >> 3][gt & 7] = 0u;
+    if (gt < kMaxAngles) Gp.homfix[gt] = 0ull;
     __syncthreads();
     if (g == 1) table_release(1);                          // the table starts out free for group 0
 
     const long long first = blockIdx.x;
     const long long mine = first < P.n_tiles ? (P.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
     const long long n_iter = (mine + 1) / 2;
-    for (long long it = 0; it < n_iter; ++it) {
+    TileWalk walk;
+    walk.init(P, first + (long long)g * gridDim.x < P.n_tiles ? first + (long long)g * gridDim.x : 0, 2ll * gridDim.x);
+    for (long long it = 0; it < n_iter; ++it, walk.next()) {
         const long long kk = 2 * it + g;
         const bool active = kk < mine;
         const long long t = first + kk * gridDim.x;
         Tile T;
         T.h = 0; T.w = 0; T.n = 0;
         if (active) {
-            T = resolve_tile(P, t);
+            T = resolve_tile_rs(P, walk.row, walk.slot);
             const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
             const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
             const int nfull = T.n >> 3, rem = T.n & 7;
@@ -227,35 +244,43 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k3_glcm_kernel(const __gr
             group_sync(g);
         }
 
-        // ---- 3. one GLCM per direction ----
-        for (int a = 0; a < P.n_angles; ++a) {
-            K3Acc A = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0};
-            K3Geom G = k3_geom(T.h, T.w, P.dr[a], P.dc[a]);
-            uint32_t I4[kK3Items], J4[kK3Items], vm[kK3Items];
-            if (active) {
-                // table-free work: pair-stream sums
-#pragma unroll
-                for (int i = 0; i < kK3Items; ++i) {
-                    const int item = gt + i * kGroupThreads;
-                    vm[i] = 0u; I4[i] = 0u; J4[i] = 0u;
-                    if (item < G.items && k3_item<MASKED>(Gp, G, item, I4[i], J4[i], vm[i]))
-                        k3_sums(S, I4[i], J4[i], vm[i], A);
-                }
-                for (int item = gt + kK3Items * kGroupThreads; item < G.items; item += kGroupThreads) {
+        // ---- 3. table-free pair-stream sums, all directions ----
+        if (active) {
+            for (int a = 0; a < P.n_angles; ++a) {
+                K3Acc A = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0};
+                const K3Geom G = k3_geom(T.h, T.w, P.dr[a], P.dc[a]);
+                for (int item = gt; item < G.items; item += kGroupThreads) {
                     uint32_t i4, j4, v;
                     if (k3_item<MASKED>(Gp, G, item, i4, j4, v)) k3_sums(S, i4, j4, v, A);
                 }
-            }
-            table_acquire(g);                              // ---- table owned by this group ----
-            if (active) {
+                uint32_t red[6] = {A.si, A.sj, A.sii, A.sjj, A.sij, A.sd};
 #pragma unroll
-                for (int i = 0; i < kK3Items; ++i)
-                    if (vm[i]) k3_bins<0>(S, I4[i], J4[i], vm[i], A.sasm);
-                for (int item = gt + kK3Items * kGroupThreads; item < G.items; item += kGroupThreads) {
-                    uint32_t i4, j4, v;
-                    if (k3_item<MASKED>(Gp, G, item, i4, j4, v)) k3_bins<0>(S, i4, j4, v, A.sasm);
+                for (int k = 0; k < 6; ++k) red[k] = __reduce_add_sync(0xffffffffu, red[k]);
+                const uint32_t mm = __reduce_add_sync(0xffffffffu, A.m);
+                // per-thread double -> 2^-40 fixed point, then exact integer sums (order independent)
+                const unsigned long long hf = warp_sum_redux((unsigned long long)__double2ll_rn(A.hom * 1099511627776.0));
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) atomicAdd(&Gp.acc[a][k], red[k]);
+                    atomicAdd(&Gp.acc[a][7], mm);
+                    atomicAdd(&Gp.homfix[a], hf);
                 }
-                group_sync(g);                             // bins complete
+            }
+        }
+
+        // ---- 4. the bins: one table ownership per tile, all directions back to back ----
+        table_acquire(g);
+        if (active) {
+            for (int a = 0; a < P.n_angles; ++a) {
+                const K3Geom G = k3_geom(T.h, T.w, P.dr[a], P.dc[a]);
+                uint32_t sold = 0u;
+                for (int item = gt; item < G.items; item += kGroupThreads) {
+                    uint32_t i4, j4, v;
+                    if (k3_item<MASKED>(Gp, G, item, i4, j4, v)) k3_bins<0>(S, i4, j4, v, sold);
+                }
+                sold = __reduce_add_sync(0xffffffffu, sold);
+                if (lane == 0) atomicAdd(&Gp.acc[a][6], sold);
+                group_sync(g);                             // bins of this direction complete
                 if (DUMP) {
                     uint32_t* dst = P.counts + (t * P.n_angles + a) * 65536ll;
                     for (int k = gt; k < 32768; k += kGroupThreads) {
@@ -264,59 +289,44 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k3_glcm_kernel(const __gr
                     }
                     group_sync(g);
                 }
-#pragma unroll
-                for (int i = 0; i < kK3Items; ++i)
-                    if (vm[i]) k3_bins<2>(S, I4[i], J4[i], vm[i], A.sasm);
-                for (int item = gt + kK3Items * kGroupThreads; item < G.items; item += kGroupThreads) {
-                    uint32_t i4, j4, v;
-                    if (k3_item<MASKED>(Gp, G, item, i4, j4, v)) k3_bins<2>(S, i4, j4, v, A.sasm);
+                for (int item = gt; item < G.items; item += kGroupThreads) {
+                    uint32_t i4, j4, v, dummy = 0u;
+                    if (k3_item<MASKED>(Gp, G, item, i4, j4, v)) k3_bins<2>(S, i4, j4, v, dummy);
+                }
+                if (a + 1 < P.n_angles) group_sync(g);     // bins clean before the next direction
+            }
+        }
+        if (!(g == 1 && it == n_iter - 1)) table_release(g);   // all of this group's clears precede it
+
+        // ---- 5. epilogue: one lane per direction ----
+        if (active) {
+            group_sync(g);                                 // accumulators complete
+            if (gw == 0 && lane < P.n_angles) {
+                const int a = lane;
+                const uint32_t* s = Gp.acc[a];
+                const long long M = (long long)s[7];
+                double* o = T.out_row + P.col_glcm + (T.slot * P.n_angles + a) * kNGlcm;
+                if (M == 0) {
+                    o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 0.0; o[4] = 0.0; o[5] = 1.0;
+                    if (T.status) atomicOr(T.status, kStNoPairs);
+                } else {
+                    const double Md = (double)M;
+                    const long long con = (long long)s[2] + (long long)s[3] - 2ll * (long long)s[4];
+                    const long long vi = M * (long long)s[2] - (long long)s[0] * (long long)s[0];
+                    const long long vj = M * (long long)s[3] - (long long)s[1] * (long long)s[1];
+                    const long long cov = M * (long long)s[4] - (long long)s[0] * (long long)s[1];
+                    const double asmv = (double)(2ull * s[6] + (unsigned long long)M) / (Md * Md);
+                    o[0] = (double)con / Md;
+                    o[1] = (double)s[5] / Md;
+                    o[2] = ((double)Gp.homfix[a] * 9.094947017729282e-13) / Md;
+                    o[3] = asmv;
+                    o[4] = sqrt(asmv);
+                    o[5] = (vi == 0 || vj == 0) ? 1.0 : (double)cov / (sqrt((double)vi) * sqrt((double)vj));
                 }
             }
-            if (!(g == 1 && it == n_iter - 1 && a == P.n_angles - 1)) table_release(g);   // ---- hand over ----
-            if (active) {
-                uint32_t red[8] = {A.si, A.sj, A.sii, A.sjj, A.sij, A.sd, A.sasm, A.m};
-#pragma unroll
-                for (int k = 0; k < 8; ++k) red[k] = __reduce_add_sync(0xffffffffu, red[k]);
-                const double hom = warp_sum(A.hom);
-                if (lane == 0) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) Gp.wred[gw][k] = red[k];
-                    Gp.whom[gw] = hom;
-                }
-                group_sync(g);                             // partials visible
-                if (gw == 0) {
-                    unsigned long long s[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        s[k] = __reduce_add_sync(0xffffffffu, lane < kGroupWarps ? Gp.wred[lane][k] : 0u);
-                    // sums of the 16 partials can exceed 32 bits only for sii/sjj/sij/sasm at the
-                    // 32768-pixel limit: 32768 * 255^2 < 2^31, and sasm <= M^2 <= 2^30 -> all fit
-                    double homt = 0.0;
-                    for (int k = 0; k < kGroupWarps; ++k) homt += Gp.whom[k];
-                    if (lane == 0) {
-                        const long long M = (long long)s[7];
-                        double* o = T.out_row + P.col_glcm + (T.slot * P.n_angles + a) * kNGlcm;
-                        if (M == 0) {
-                            o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 0.0; o[4] = 0.0; o[5] = 1.0;
-                            if (T.status) atomicOr(T.status, kStNoPairs);
-                        } else {
-                            const double Md = (double)M;
-                            const long long con = (long long)s[2] + (long long)s[3] - 2ll * (long long)s[4];
-                            const long long vi = M * (long long)s[2] - (long long)s[0] * (long long)s[0];
-                            const long long vj = M * (long long)s[3] - (long long)s[1] * (long long)s[1];
-                            const long long cov = M * (long long)s[4] - (long long)s[0] * (long long)s[1];
-                            const double asmv = (double)(2ull * s[6] + (unsigned long long)M) / (Md * Md);
-                            o[0] = (double)con / Md;
-                            o[1] = (double)s[5] / Md;
-                            o[2] = homt / Md;
-                            o[3] = asmv;
-                            o[4] = sqrt(asmv);
-                            o[5] = (vi == 0 || vj == 0) ? 1.0 : (double)cov / (sqrt((double)vi) * sqrt((double)vj));
-                        }
-                    }
-                }
-                group_sync(g);                             // partials consumed before the next direction
-            }
+            group_sync(g);                                 // accumulators consumed
+            if (gt < kMaxAngles * 8) Gp.acc[gt >> 3][gt & 7] = 0u;
+            if (gt < kMaxAngles) Gp.homfix[gt] = 0ull;
         }
     }
 }

@@ -33,16 +33,6 @@ struct K4Smem {
     } u;
 };
 
-// exact warp sum of 64-bit integers with three 21-bit limbs (REDUX.ADD is one instruction)
-__device__ __forceinline__ unsigned long long warp_sum_redux(unsigned long long v) {
-    const uint32_t l0 = (uint32_t)v & 0x1fffffu, l1 = (uint32_t)(v >> 21) & 0x1fffffu;
-    const uint32_t l2 = (uint32_t)(v >> 42);
-    const unsigned long long s0 = __reduce_add_sync(0xffffffffu, l0);
-    const unsigned long long s1 = __reduce_add_sync(0xffffffffu, l1);
-    const unsigned long long s2 = __reduce_add_sync(0xffffffffu, l2);
-    return s0 + (s1 << 21) + (s2 << 42);
-}
-
 __device__ __forceinline__ double i128_to_double(__int128 v) {
     const bool neg = v < 0;
     const unsigned __int128 a = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
@@ -125,8 +115,10 @@ __global__ void __launch_bounds__(kK4Threads) k4_shape_kernel(const __grid_const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool want_mom = P.col_moment >= 0;
 
-    for (long long t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
-        const Tile T = resolve_tile(P, t);
+    TileWalk walk;
+    walk.init(P, blockIdx.x < P.n_tiles ? blockIdx.x : 0, gridDim.x);
+    for (long long t = blockIdx.x; t < P.n_tiles; t += gridDim.x, walk.next()) {
+        const Tile T = resolve_tile_rs(P, walk.row, walk.slot);
         const int h = T.h, w = T.w, n = T.n;
         unsigned long long a[kK4NInt];
 #pragma unroll
@@ -138,42 +130,60 @@ __global__ void __launch_bounds__(kK4Threads) k4_shape_kernel(const __grid_const
 
         if (fast) {
             const int Pw = (w + 31) >> 5;                  // mask words per row
-            uint32_t area = 0, sr = 0, sc = 0, srr = 0, scc = 0, src = 0, m00 = 0;
-            unsigned long long m10 = 0, m01 = 0, m20 = 0, m11 = 0, m02 = 0, m30 = 0, m21 = 0, m12 = 0, m03 = 0;
-            // ---- pass A: one warp per row, lanes over columns ----
-            for (int r = warp; r < h; r += kK4Warps) {
-                const uint32_t r1 = r, r2 = r * r, r3 = r2 * r;
-                for (int c0 = 0; c0 < w; c0 += 32) {
-                    const int c = c0 + lane;
-                    const int i = r * w + c;
-                    const bool m = c < w && (!MASKED || T.mk[i] != 0);
-                    const uint32_t bal = __ballot_sync(0xffffffffu, m);
-                    if (lane == 0) S.u.fast.mrow[r * Pw + (c0 >> 5)] = bal;
-                    if (m) {
-                        area += 1; sr += r1; srr += r2; sc += c; scc += c * c; src += r1 * c;
-                        rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
-                        if (want_mom) {
-                            const uint32_t v0 = T.px[i];
-                            const uint32_t v1 = v0 * (uint32_t)c, v2 = v1 * (uint32_t)c;
-                            const unsigned long long v3 = (unsigned long long)v2 * (uint32_t)c;
-                            m00 += v0;
-                            m10 += (unsigned long long)v0 * r1; m20 += (unsigned long long)v0 * r2;
-                            m30 += (unsigned long long)v0 * r3;
-                            m01 += v1; m11 += (unsigned long long)v1 * r1; m21 += (unsigned long long)v1 * r2;
-                            m02 += v2; m12 += (unsigned long long)v2 * r1;
-                            m03 += v3;
-                        }
+            // ---- pass A: warps over rows, lanes over columns.  Row sums are accumulated per lane
+            //      for one 32-column block at a time and folded with the (lane-constant) column
+            //      index afterwards: M_pq = sum_c c^q * (sum_r r^p * I[r][c]) ----
+            uint32_t area = 0, sr = 0, sc = 0, srr = 0, scc = 0, src = 0;
+            unsigned long long mq[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // M00 M10 M01 M20 M11 M02 M30 M21 M12 M03
+            for (int c0 = 0; c0 < w; c0 += 32) {
+                const int c = c0 + lane;
+                const bool inb = c < w;
+                uint32_t cnt = 0, csr = 0, csrr = 0, b0 = 0, b1 = 0;
+                unsigned long long b2 = 0, b3 = 0;
+                int r = warp;
+                for (; r < h; r += kK4Warps * 4) {
+                    uint32_t mk[4], px[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {         // issue the loads of four rows first
+                        const int ru = r + u * kK4Warps;
+                        const int i = ru * w + c;
+                        const bool ok = inb && ru < h;
+                        mk[u] = ok ? (MASKED ? (uint32_t)T.mk[i] : 1u) : 0u;
+                        px[u] = (ok && want_mom) ? (uint32_t)T.px[i] : 0u;
                     }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int ru = r + u * kK4Warps;
+                        if (ru >= h) break;                // warp-uniform
+                        const bool m = mk[u] != 0u;
+                        const uint32_t bal = __ballot_sync(0xffffffffu, m);
+                        if (lane == 0) S.u.fast.mrow[ru * Pw + (c0 >> 5)] = bal;
+                        const uint32_t m1 = m ? 1u : 0u, im = m ? px[u] : 0u;
+                        const uint32_t r1 = ru, r2 = ru * ru, r3 = r2 * ru;
+                        cnt += m1; csr += m1 * r1; csrr += m1 * r2;
+                        if (m) { rmin = min(rmin, ru); rmax = max(rmax, ru); }
+                        b0 += im; b1 += im * r1;
+                        b2 += (unsigned long long)im * r2;
+                        b3 += (unsigned long long)im * r3;
+                    }
+                }
+                if (cnt) { cmin = min(cmin, c); cmax = max(cmax, c); }
+                const uint32_t c1 = inb ? c : 0, c2 = c1 * c1, c3 = c2 * c1;
+                area += cnt; sr += csr; srr += csrr; sc += c1 * cnt; scc += c2 * cnt; src += c1 * csr;
+                if (want_mom) {
+                    mq[0] += b0; mq[1] += b1; mq[3] += b2; mq[6] += b3;
+                    mq[2] += (unsigned long long)b0 * c1; mq[4] += (unsigned long long)b1 * c1;
+                    mq[7] += b2 * c1;
+                    mq[5] += (unsigned long long)b0 * c2; mq[8] += (unsigned long long)b1 * c2;
+                    mq[9] += (unsigned long long)b0 * c3;
                 }
             }
             a[0] = __reduce_add_sync(0xffffffffu, area); a[1] = __reduce_add_sync(0xffffffffu, sr);
             a[2] = __reduce_add_sync(0xffffffffu, sc);   a[3] = __reduce_add_sync(0xffffffffu, srr);
             a[4] = __reduce_add_sync(0xffffffffu, scc);  a[5] = __reduce_add_sync(0xffffffffu, src);
             if (want_mom) {
-                a[9] = __reduce_add_sync(0xffffffffu, m00);
-                a[10] = warp_sum_redux(m10); a[11] = warp_sum_redux(m01); a[12] = warp_sum_redux(m20);
-                a[13] = warp_sum_redux(m11); a[14] = warp_sum_redux(m02); a[15] = warp_sum_redux(m30);
-                a[16] = warp_sum_redux(m21); a[17] = warp_sum_redux(m12); a[18] = warp_sum_redux(m03);
+#pragma unroll
+                for (int k = 0; k < 10; ++k) a[9 + k] = warp_sum_redux(mq[k]);
             }
             __syncthreads();                               // mask rows complete
             // ---- pass B: border = mask & ~erosion4(mask), 32 pixels per word ----
