@@ -132,6 +132,48 @@ __device__ __forceinline__ void group_sync(int g) { bar_sync(1 + g, kGroupThread
 __device__ __forceinline__ void table_acquire(int g) { bar_sync(3 + g, kPingPongThreads); }
 __device__ __forceinline__ void table_release(int g) { bar_arrive(3 + (g ^ 1), kPingPongThreads); }
 
+// ---- Token ring over one shared-memory table (K2, K3) -------------------------------------------
+// The 65,536-bin table leaves room for one CTA per SM.  Its 1,024 threads are split into NG
+// groups (2, 4 or 8) that work on NG different tiles; the table is handed round-robin from group
+// to group through mbarriers: token[g] completes a phase when every thread of group g-1 has
+// arrived (after its last table access), and group g waits on it before its first access.  All
+// table-free work of a group overlaps the other groups' table phases.
+struct Ring {
+    int g, ng, gthreads, gt, gw, gwarps;
+    uint32_t tok_mine, tok_next;   // shared-window addresses of token[g], token[(g+1) % ng]
+    uint32_t parity;               // parity of the phase this group waits for next
+};
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ring_init(Ring& R, unsigned long long* tokens, int ng) {
+    const int tid = threadIdx.x;
+    R.ng = ng;
+    R.gthreads = blockDim.x / ng;
+    R.g = tid / R.gthreads;
+    R.gt = tid - R.g * R.gthreads;
+    R.gw = R.gt >> 5;
+    R.gwarps = R.gthreads >> 5;
+    R.tok_mine = smem_addr(tokens + R.g);
+    R.tok_next = smem_addr(tokens + (R.g + 1 == ng ? 0 : R.g + 1));
+    R.parity = R.g == 0 ? 1u : 0u;     // group 0 owns the table first (phase "-1" counts as complete)
+    if (tid < ng)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(tokens + tid)), "r"(R.gthreads));
+}
+__device__ __forceinline__ void ring_acquire(Ring& R) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(R.tok_mine), "r"(R.parity)
+        : "memory");
+    R.parity ^= 1u;
+}
+__device__ __forceinline__ void ring_release(const Ring& R) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(R.tok_next) : "memory");
+}
+__device__ __forceinline__ void ring_group_sync(const Ring& R) { bar_sync(1 + R.g, R.gthreads); }
+
 // exact warp sum of 64-bit integers with three 21-bit limbs (REDUX.ADD is one instruction)
 __device__ __forceinline__ unsigned long long warp_sum_redux(unsigned long long v) {
     const uint32_t l0 = (uint32_t)v & 0x1fffffu, l1 = (uint32_t)(v >> 21) & 0x1fffffu;

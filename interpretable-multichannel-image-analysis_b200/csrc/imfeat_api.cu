@@ -136,10 +136,10 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
     free(tab);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_order_entropy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_order_entropy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k4_shape_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k4_shape_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_bps[0], k1_moments_kernel<false>, 256, 0);
@@ -186,6 +186,16 @@ int imfeat_destroy(imfeat_ctx* ctx) {
 }
 
 }  // extern "C"
+
+// Number of thread groups sharing the GLCM table: more groups = more tiles in flight and less fixed
+// per-thread overhead per pair, limited by the per-group staging of the quantised tile.
+static int k3_groups(int max_pixels) {
+    const char* env = getenv("IMFEAT_K3_GROUPS");
+    int want = env ? atoi(env) : 4;
+    if (want != 2 && want != 4 && want != 8) want = 4;
+    while (want > 2 && k3_smem_bytes(max_pixels, want) > 220 * 1024) want /= 2;
+    return want;
+}
 
 // C round(): half away from zero, as skimage's _glcm_loop uses for the pixel offsets.
 static int c_round(double v) { return (int)(v < 0 ? -floor(-v + 0.5) : floor(v + 0.5)); }
@@ -296,8 +306,10 @@ static int launch_all(imfeat_ctx* ctx, const Params& P, const imfeat_opts* o, cu
     }
     if (o->want_glcm) {
         const int g3 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
-        if (masked) k3_glcm_kernel<true, false><<<g3, kPingPongThreads, sizeof(K3Smem), st>>>(P);
-        else k3_glcm_kernel<false, false><<<g3, kPingPongThreads, sizeof(K3Smem), st>>>(P);
+        const int maxpx = ((P.hs * P.ws + 7) & ~7);
+        const int ng3 = k3_groups(maxpx);
+        if (masked) k3_glcm_kernel<true, false><<<g3, 1024, k3_smem_bytes(maxpx, ng3), st>>>(P, ng3, maxpx);
+        else k3_glcm_kernel<false, false><<<g3, 1024, k3_smem_bytes(maxpx, ng3), st>>>(P, ng3, maxpx);
         IMFEAT_MARK(2)
         ctx->launches += 1;
     }
@@ -383,8 +395,10 @@ int imfeat_glcm_counts_device(imfeat_ctx* ctx, const uint16_t* d_planes, const u
                 plane_stride, &o, scratch, width, nullptr);
     P.counts = d_counts;
     const int g3 = (int)(P.n_tiles < ctx->sm_count ? P.n_tiles : ctx->sm_count);
-    if (d_masks) k3_glcm_kernel<true, true><<<g3, kPingPongThreads, sizeof(K3Smem), st>>>(P);
-    else k3_glcm_kernel<false, true><<<g3, kPingPongThreads, sizeof(K3Smem), st>>>(P);
+    const int maxpx = ((P.hs * P.ws + 7) & ~7);
+    const int ng3 = k3_groups(maxpx);
+    if (d_masks) k3_glcm_kernel<true, true><<<g3, 1024, k3_smem_bytes(maxpx, ng3), st>>>(P, ng3, maxpx);
+    else k3_glcm_kernel<false, true><<<g3, 1024, k3_smem_bytes(maxpx, ng3), st>>>(P, ng3, maxpx);
     ctx->launches += 1;
     CU(cudaGetLastError());
     CU(cudaFreeAsync(scratch, st));

@@ -23,18 +23,32 @@
 namespace imfeat {
 
 
-struct K3Group {
+constexpr int kK3Cache = 4;     // pair groups (4 pairs each) per thread cached in registers
+
+// Shared-memory layout (dynamic): [hist 128 KB][homtab 2 KB][tokens][per-group: K3GroupHdr, q8, mbits]
+struct K3GroupHdr {
     unsigned long long homfix[kMaxAngles];     // sum 1/(1+d^2) in 2^-40 fixed point, per direction
     uint32_t acc[kMaxAngles][8];               // si sj sii sjj sij sd sold m, per direction
-    uint32_t wmax[kGroupWarps];
-    uint32_t q8[kMaxPixels / 4 + 4];      // quantised pixels (bytes) + slack for unaligned reads
-    uint32_t mbits[kMaxPixels / 32 + 2];  // one bit per pixel: inside the mask (masked variant)
+    uint32_t wmax[32];
 };
 struct K3Smem {
     uint32_t hist[32768];
+    uint32_t dummy[2];       // bin for the non-existent pairs of a partial group (unmasked path), at hist + 0x20000
     double homtab[256];
-    K3Group grp[2];
+    unsigned long long tokens[8];
 };
+struct K3Group {                               // pointers into the dynamic region of this group
+    K3GroupHdr* hdr;
+    uint32_t* q8;                              // quantised pixels (bytes) + slack for unaligned reads
+    uint32_t* mbits;                           // one bit per pixel: inside the mask (masked variant)
+};
+__host__ __device__ inline size_t k3_group_bytes(int max_pixels) {
+    const size_t q8w = (size_t)max_pixels / 4 + 4, mbw = (size_t)max_pixels / 32 + 2;
+    return sizeof(K3GroupHdr) + 4 * ((q8w + 1) & ~(size_t)1) + 4 * ((mbw + 1) & ~(size_t)1);
+}
+__host__ __device__ inline size_t k3_smem_bytes(int max_pixels, int ng) {
+    return sizeof(K3Smem) + (size_t)ng * k3_group_bytes(max_pixels);
+}
 
 struct K3Acc {
     uint32_t si, sj, sii, sjj, sij, sd, sasm, m;
@@ -104,6 +118,10 @@ __device__ __forceinline__ bool k3_item(const K3Group& Gp, const K3Geom& G, int 
     return vm != 0u;
 }
 
+// Pair-stream sums of one item.  Unmasked tiles run branch-free: the bytes of non-existent pairs
+// (row tails) are zero, so they add nothing to the integer sums and exactly homtab[0] = 1.0 to the
+// homogeneity sum, which the epilogue subtracts again.
+template <bool MASKED>
 __device__ __forceinline__ void k3_sums(const K3Smem& S, uint32_t I4, uint32_t J4, uint32_t vm, K3Acc& A) {
     A.si = __dp4a(I4, 0x01010101u, A.si);
     A.sj = __dp4a(J4, 0x01010101u, A.sj);
@@ -113,7 +131,7 @@ __device__ __forceinline__ void k3_sums(const K3Smem& S, uint32_t I4, uint32_t J
     A.sd += __vsadu4(I4, J4);
     A.m += __popc(vm) >> 3;
     const uint32_t D4 = __vabsdiffu4(I4, J4);
-    if (vm == 0xffffffffu) {
+    if (!MASKED) {
         A.hom += S.homtab[D4 & 0xffu];
         A.hom += S.homtab[(D4 >> 8) & 0xffu];
         A.hom += S.homtab[(D4 >> 16) & 0xffu];
@@ -127,55 +145,65 @@ __device__ __forceinline__ void k3_sums(const K3Smem& S, uint32_t I4, uint32_t J
 
 // PHASE 0: bins += 1, accumulating the returned old counts (sum_bins c^2 = 2*sum(old) + M);
 // PHASE 2: sparse clear.  Keys (i << 8 | j) are assembled two at a time with PRMT.
-template <int PHASE>
-__device__ __forceinline__ void k3_bin1(K3Smem& S, uint32_t key, uint32_t& sold) {
-    uint32_t* word = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(S.hist) + ((key << 1) & 0x1fffcu));
+// Unmasked tiles run branch-free: a non-existent pair is redirected to the dummy bin behind the
+// table; D such pairs return the old values 0..D-1 in some order, so the epilogue subtracts
+// D(D-1)/2.  Masked tiles (many missing pairs) use predication instead.
+template <int PHASE, bool MASKED>
+__device__ __forceinline__ void k3_bin1(K3Smem& S, uint32_t key, bool exists, uint32_t& sold) {
+    if (MASKED && !exists) return;
+    uint32_t off = (key << 1) & 0x1fffcu;
+    if (!MASKED) off = exists ? off : 0x20000u;
+    uint32_t* word = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(S.hist) + off);
     if (PHASE == 0) {
-        const uint32_t sh = (key & 1u) << 4;
+        const uint32_t sh = (key & 1u) << 4;       // key == 0 for a non-existent pair
         sold += (atomicAdd(word, 1u << sh) >> sh) & 0xffffu;
     } else {
         *word = 0u;
     }
 }
-template <int PHASE>
+template <int PHASE, bool MASKED>
 __device__ __forceinline__ void k3_bins(K3Smem& S, uint32_t I4, uint32_t J4, uint32_t vm, uint32_t& sold) {
     const uint32_t K01 = __byte_perm(J4, I4, 0x5140);   // [j0, i0, j1, i1]
     const uint32_t K23 = __byte_perm(J4, I4, 0x7362);   // [j2, i2, j3, i3]
-    if (vm == 0xffffffffu) {
-        k3_bin1<PHASE>(S, K01 & 0xffffu, sold);
-        k3_bin1<PHASE>(S, K01 >> 16, sold);
-        k3_bin1<PHASE>(S, K23 & 0xffffu, sold);
-        k3_bin1<PHASE>(S, K23 >> 16, sold);
-        return;
-    }
-    if (vm & 0x00000001u) k3_bin1<PHASE>(S, K01 & 0xffffu, sold);
-    if (vm & 0x00000100u) k3_bin1<PHASE>(S, K01 >> 16, sold);
-    if (vm & 0x00010000u) k3_bin1<PHASE>(S, K23 & 0xffffu, sold);
-    if (vm & 0x01000000u) k3_bin1<PHASE>(S, K23 >> 16, sold);
+    k3_bin1<PHASE, MASKED>(S, K01 & 0xffffu, (vm & 0x00000001u) != 0u, sold);
+    k3_bin1<PHASE, MASKED>(S, K01 >> 16, (vm & 0x00000100u) != 0u, sold);
+    k3_bin1<PHASE, MASKED>(S, K23 & 0xffffu, (vm & 0x00010000u) != 0u, sold);
+    k3_bin1<PHASE, MASKED>(S, K23 >> 16, (vm & 0x01000000u) != 0u, sold);
 }
 
 template <bool MASKED, bool DUMP>
-__global__ void __launch_bounds__(kPingPongThreads, 1) k3_glcm_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant__ Params P, int ng, int max_pixels) {
     extern __shared__ __align__(16) unsigned char k3_smem_raw[];
     K3Smem& S = *reinterpret_cast<K3Smem*>(k3_smem_raw);
-    const int tid = threadIdx.x, g = tid / kGroupThreads, gt = tid % kGroupThreads;
-    const int lane = tid & 31, gw = gt >> 5;
-    K3Group& Gp = S.grp[g];
+    const int tid = threadIdx.x, lane = tid & 31;
+    Ring R;
+    ring_init(R, S.tokens, ng);
+    const int g = R.g, gt = R.gt, gw = R.gw, gthreads = R.gthreads;
+    K3Group Gp;
+    {
+        unsigned char* base = k3_smem_raw + sizeof(K3Smem) + (size_t)g * k3_group_bytes(max_pixels);
+        const size_t q8w = ((size_t)max_pixels / 4 + 4 + 1) & ~(size_t)1;
+        Gp.hdr = reinterpret_cast<K3GroupHdr*>(base);
+        Gp.q8 = reinterpret_cast<uint32_t*>(base + sizeof(K3GroupHdr));
+        Gp.mbits = Gp.q8 + q8w;
+    }
+    K3GroupHdr& H = *Gp.hdr;
 
-    for (int k = tid; k < 32768; k += kPingPongThreads) S.hist[k] = 0u;
+    for (int k = tid; k < 32768; k += blockDim.x) S.hist[k] = 0u;
     if (tid < 256) S.homtab[tid] = 1.0 / (1.0 + (double)(tid * tid));
-    if (gt < kMaxAngles * 8) Gp.acc[gt >> 3][gt & 7] = 0u;
-    if (gt < kMaxAngles) Gp.homfix[gt] = 0ull;
+    if (tid < 2) S.dummy[tid] = 0u;
+    if (gt < kMaxAngles * 8) H.acc[gt >> 3][gt & 7] = 0u;
+    if (gt < kMaxAngles) H.homfix[gt] = 0ull;
     __syncthreads();
-    if (g == 1) table_release(1);                          // the table starts out free for group 0
 
     const long long first = blockIdx.x;
     const long long mine = first < P.n_tiles ? (P.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
-    const long long n_iter = (mine + 1) / 2;
+    const long long n_iter = (mine + ng - 1) / ng;
     TileWalk walk;
-    walk.init(P, first + (long long)g * gridDim.x < P.n_tiles ? first + (long long)g * gridDim.x : 0, 2ll * gridDim.x);
+    walk.init(P, first + (long long)g * gridDim.x < P.n_tiles ? first + (long long)g * gridDim.x : 0,
+              (long long)ng * gridDim.x);
     for (long long it = 0; it < n_iter; ++it, walk.next()) {
-        const long long kk = 2 * it + g;
+        const long long kk = (long long)ng * it + g;
         const bool active = kk < mine;
         const long long t = first + kk * gridDim.x;
         Tile T;
@@ -189,7 +217,7 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k3_glcm_kernel(const __gr
 
             // ---- 1. tile maximum (over the mask when masked); stage the mask bits ----
             uint32_t mx2 = 0u;
-            for (int idx = gt; idx < nfull; idx += kGroupThreads) {
+            for (int idx = gt; idx < nfull; idx += gthreads) {
                 uint4 v = ld_reuse(px4 + idx);
                 if (MASKED) {
                     const uint2 m = __ldg(mk2 + idx);
@@ -213,9 +241,9 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k3_glcm_kernel(const __gr
                 if (MASKED) mbytes[nfull] = (uint8_t)bits;
             }
             const uint32_t wm = __reduce_max_sync(0xffffffffu, max(mx2 & 0xffffu, mx2 >> 16));
-            if (lane == 0) Gp.wmax[gw] = wm;
-            group_sync(g);
-            uint32_t vmax = lane < kGroupWarps ? Gp.wmax[lane] : 0u;
+            if (lane == 0) H.wmax[gw] = wm;
+            ring_group_sync(R);
+            uint32_t vmax = lane < R.gwarps ? H.wmax[lane] : 0u;
             vmax = __reduce_max_sync(0xffffffffu, vmax);
 
             // ---- 2. quantise to 8 bits into shared memory ----
@@ -223,7 +251,7 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k3_glcm_kernel(const __gr
             if (lane == 0) k3_magic(vmax, mul, sh);
             mul = __shfl_sync(0xffffffffu, mul, 0);
             sh = __shfl_sync(0xffffffffu, sh, 0);
-            for (int idx = gt; idx < nfull; idx += kGroupThreads) {
+            for (int idx = gt; idx < nfull; idx += gthreads) {
                 const uint4 v = ld_reuse(px4 + idx);
                 const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
                 uint32_t q[2] = {0u, 0u};
@@ -234,24 +262,32 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k3_glcm_kernel(const __gr
                     if (MASKED) { a = min(a, 255u); b = min(b, 255u); }
                     q[k >> 1] |= (a | (b << 8)) << (16 * (k & 1));
                 }
-                Gp.q8[2 * idx] = q[0];
-                Gp.q8[2 * idx + 1] = q[1];
+                *reinterpret_cast<uint2*>(Gp.q8 + 2 * idx) = make_uint2(q[0], q[1]);
             }
             if (gt < rem) {
                 const int i = nfull * 8 + gt;
                 reinterpret_cast<uint8_t*>(Gp.q8)[i] = (uint8_t)min(k3_quant(T.px[i], mul, sh), 255u);
             }
-            group_sync(g);
+            ring_group_sync(R);
         }
 
-        // ---- 3. table-free pair-stream sums, all directions ----
-        if (active) {
-            for (int a = 0; a < P.n_angles; ++a) {
+        // ---- 3. one GLCM per direction ----
+        for (int a = 0; a < P.n_angles; ++a) {
+            const K3Geom G = k3_geom(T.h, T.w, P.dr[a], P.dc[a]);
+            uint32_t I4[kK3Cache], J4[kK3Cache], vm[kK3Cache];
+            if (active) {
+                // table-free: pair-stream sums; the first kK3Cache items of a thread stay in registers
                 K3Acc A = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0};
-                const K3Geom G = k3_geom(T.h, T.w, P.dr[a], P.dc[a]);
-                for (int item = gt; item < G.items; item += kGroupThreads) {
+#pragma unroll
+                for (int i = 0; i < kK3Cache; ++i) {
+                    const int item = gt + i * gthreads;
+                    vm[i] = 0u; I4[i] = 0u; J4[i] = 0u;
+                    if (item < G.items && k3_item<MASKED>(Gp, G, item, I4[i], J4[i], vm[i]))
+                        k3_sums<MASKED>(S, I4[i], J4[i], vm[i], A);
+                }
+                for (int item = gt + kK3Cache * gthreads; item < G.items; item += gthreads) {
                     uint32_t i4, j4, v;
-                    if (k3_item<MASKED>(Gp, G, item, i4, j4, v)) k3_sums(S, i4, j4, v, A);
+                    if (k3_item<MASKED>(Gp, G, item, i4, j4, v)) k3_sums<MASKED>(S, i4, j4, v, A);
                 }
                 uint32_t red[6] = {A.si, A.sj, A.sii, A.sjj, A.sij, A.sd};
 #pragma unroll
@@ -261,50 +297,58 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k3_glcm_kernel(const __gr
                 const unsigned long long hf = warp_sum_redux((unsigned long long)__double2ll_rn(A.hom * 1099511627776.0));
                 if (lane == 0) {
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) atomicAdd(&Gp.acc[a][k], red[k]);
-                    atomicAdd(&Gp.acc[a][7], mm);
-                    atomicAdd(&Gp.homfix[a], hf);
+                    for (int k = 0; k < 6; ++k) atomicAdd(&H.acc[a][k], red[k]);
+                    atomicAdd(&H.acc[a][7], mm);
+                    atomicAdd(&H.homfix[a], hf);
                 }
             }
-        }
-
-        // ---- 4. the bins: one table ownership per tile, all directions back to back ----
-        table_acquire(g);
-        if (active) {
-            for (int a = 0; a < P.n_angles; ++a) {
-                const K3Geom G = k3_geom(T.h, T.w, P.dr[a], P.dc[a]);
+            ring_acquire(R);                               // ---- table owned by this group ----
+            if (active) {
                 uint32_t sold = 0u;
-                for (int item = gt; item < G.items; item += kGroupThreads) {
+#pragma unroll
+                for (int i = 0; i < kK3Cache; ++i)
+                    if (vm[i]) k3_bins<0, MASKED>(S, I4[i], J4[i], vm[i], sold);
+                for (int item = gt + kK3Cache * gthreads; item < G.items; item += gthreads) {
                     uint32_t i4, j4, v;
-                    if (k3_item<MASKED>(Gp, G, item, i4, j4, v)) k3_bins<0>(S, i4, j4, v, sold);
+                    if (k3_item<MASKED>(Gp, G, item, i4, j4, v)) k3_bins<0, MASKED>(S, i4, j4, v, sold);
                 }
-                sold = __reduce_add_sync(0xffffffffu, sold);
-                if (lane == 0) atomicAdd(&Gp.acc[a][6], sold);
-                group_sync(g);                             // bins of this direction complete
+                ring_group_sync(R);                        // bins complete
                 if (DUMP) {
                     uint32_t* dst = P.counts + (t * P.n_angles + a) * 65536ll;
-                    for (int k = gt; k < 32768; k += kGroupThreads) {
+                    for (int k = gt; k < 32768; k += gthreads) {
                         const uint32_t wv = S.hist[k];
                         reinterpret_cast<uint2*>(dst)[k] = make_uint2(wv & 0xffffu, wv >> 16);
                     }
-                    group_sync(g);
+                    ring_group_sync(R);
                 }
-                for (int item = gt; item < G.items; item += kGroupThreads) {
-                    uint32_t i4, j4, v, dummy = 0u;
-                    if (k3_item<MASKED>(Gp, G, item, i4, j4, v)) k3_bins<2>(S, i4, j4, v, dummy);
+                uint32_t dummy = 0u;
+#pragma unroll
+                for (int i = 0; i < kK3Cache; ++i)
+                    if (vm[i]) k3_bins<2, MASKED>(S, I4[i], J4[i], vm[i], dummy);
+                for (int item = gt + kK3Cache * gthreads; item < G.items; item += gthreads) {
+                    uint32_t i4, j4, v;
+                    if (k3_item<MASKED>(Gp, G, item, i4, j4, v)) k3_bins<2, MASKED>(S, i4, j4, v, dummy);
                 }
-                if (a + 1 < P.n_angles) group_sync(g);     // bins clean before the next direction
+                ring_release(R);                           // ---- hand the table to the next group ----
+                sold = __reduce_add_sync(0xffffffffu, sold);
+                if (lane == 0) atomicAdd(&H.acc[a][6], sold);
+            } else {
+                ring_release(R);
             }
         }
-        if (!(g == 1 && it == n_iter - 1)) table_release(g);   // all of this group's clears precede it
 
-        // ---- 5. epilogue: one lane per direction ----
+        // ---- 4. epilogue: one lane per direction ----
         if (active) {
-            group_sync(g);                                 // accumulators complete
+            ring_group_sync(R);                            // accumulators complete
             if (gw == 0 && lane < P.n_angles) {
                 const int a = lane;
-                const uint32_t* s = Gp.acc[a];
+                const uint32_t* s = H.acc[a];
                 const long long M = (long long)s[7];
+                // non-existent pairs that went through the branch-free path (unmasked only)
+                const K3Geom Ge = k3_geom(T.h, T.w, P.dr[a], P.dc[a]);
+                const long long D = MASKED ? 0ll : 4ll * Ge.nrows * Ge.gpr - M;
+                const unsigned long long sold_true = (unsigned long long)s[6] - (unsigned long long)(D * (D - 1) / 2);
+                const unsigned long long hom_true = H.homfix[a] - ((unsigned long long)D << 40);
                 double* o = T.out_row + P.col_glcm + (T.slot * P.n_angles + a) * kNGlcm;
                 if (M == 0) {
                     o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 0.0; o[4] = 0.0; o[5] = 1.0;
@@ -315,18 +359,18 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k3_glcm_kernel(const __gr
                     const long long vi = M * (long long)s[2] - (long long)s[0] * (long long)s[0];
                     const long long vj = M * (long long)s[3] - (long long)s[1] * (long long)s[1];
                     const long long cov = M * (long long)s[4] - (long long)s[0] * (long long)s[1];
-                    const double asmv = (double)(2ull * s[6] + (unsigned long long)M) / (Md * Md);
+                    const double asmv = (double)(2ull * sold_true + (unsigned long long)M) / (Md * Md);
                     o[0] = (double)con / Md;
                     o[1] = (double)s[5] / Md;
-                    o[2] = ((double)Gp.homfix[a] * 9.094947017729282e-13) / Md;
+                    o[2] = ((double)hom_true * 9.094947017729282e-13) / Md;
                     o[3] = asmv;
                     o[4] = sqrt(asmv);
                     o[5] = (vi == 0 || vj == 0) ? 1.0 : (double)cov / (sqrt((double)vi) * sqrt((double)vj));
                 }
             }
-            group_sync(g);                                 // accumulators consumed
-            if (gt < kMaxAngles * 8) Gp.acc[gt >> 3][gt & 7] = 0u;
-            if (gt < kMaxAngles) Gp.homfix[gt] = 0ull;
+            ring_group_sync(R);                            // accumulators consumed
+            if (gt < kMaxAngles * 8) H.acc[gt >> 3][gt & 7] = 0u;
+            if (gt < kMaxAngles) H.homfix[gt] = 0ull;
         }
     }
 }
