@@ -197,6 +197,12 @@ static int k3_groups(int max_pixels) {
     return want;
 }
 
+static int k2_groups() {
+    const char* env = getenv("IMFEAT_K2_GROUPS");
+    const int want = env ? atoi(env) : 2;
+    return (want == 2 || want == 4 || want == 8) ? want : 2;
+}
+
 // C round(): half away from zero, as skimage's _glcm_loop uses for the pixel offsets.
 static int c_round(double v) { return (int)(v < 0 ? -floor(-v + 0.5) : floor(v + 0.5)); }
 
@@ -299,8 +305,9 @@ static int launch_all(imfeat_ctx* ctx, const Params& P, const imfeat_opts* o, cu
         else k1_moments_kernel<false><<<g1, 256, 0, st>>>(P);
         IMFEAT_MARK(0)
         const int g2 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
-        if (masked) k2_order_entropy_kernel<true><<<g2, kPingPongThreads, sizeof(K2Smem), st>>>(P);
-        else k2_order_entropy_kernel<false><<<g2, kPingPongThreads, sizeof(K2Smem), st>>>(P);
+        const int ng2 = k2_groups();
+        if (masked) k2_order_entropy_kernel<true><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2);
+        else k2_order_entropy_kernel<false><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2);
         IMFEAT_MARK(1)
         ctx->launches += 2;
     }

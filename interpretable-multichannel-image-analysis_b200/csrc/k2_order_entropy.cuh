@@ -18,18 +18,19 @@
 
 namespace imfeat {
 
-constexpr int kK2Vec = 2;      // 16-byte vectors per thread kept in registers (n <= 8192)
+constexpr int kK2Vec = 2;      // 16-byte vectors per thread kept in registers (pixels + returned counts)
 
 struct K2Group {
     uint32_t coarse[32];     // bit b of word s: some pixel has a value in [64*(32*s+b), +64)
     int vals[18];
-    uint32_t wcnt[kGroupWarps];
-    unsigned long long wpart[kGroupWarps];
+    uint32_t cnt;            // masked pixel count (integer atomics)
     int constant;
+    unsigned long long acc;  // sum of G[old] in 2^-42 fixed point (integer atomics)
 };
 struct K2Smem {
     uint32_t hist[32768];
-    K2Group grp[2];
+    unsigned long long tokens[8];
+    K2Group grp[8];
 };
 
 // returns the count of x BEFORE this increment
@@ -59,10 +60,14 @@ __device__ __forceinline__ void k2_range(const uint4& v, const uint2& m, uint32_
 }
 
 // PHASE 0: histogram build + entropy terms, 2: sparse clear.
+// olds (optional): the returned counts of the 8 pixels, packed 2 x 16 bit per word; when given,
+// the entropy-table look-ups are left to the caller (after the table has been handed over).
 template <int PHASE, bool MASKED>
 __device__ __forceinline__ void k2_vec(K2Smem& S, const Params& P, const uint4& v, const uint2& m,
-                                       uint32_t& cnt, uint32_t& maxold, unsigned long long& acc) {
+                                       uint32_t& cnt, uint32_t& maxold, unsigned long long& acc,
+                                       uint32_t* olds = nullptr) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (PHASE == 0 && olds) { olds[0] = olds[1] = olds[2] = olds[3] = 0u; }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint32_t mb = (k < 2 ? m.x : m.y) >> (16 * (k & 1));
@@ -72,8 +77,12 @@ __device__ __forceinline__ void k2_vec(K2Smem& S, const Params& P, const uint4& 
             if (MASKED && !(mb & (hlf ? 0xff00u : 0xffu))) continue;
             if (PHASE == 0) {
                 const uint32_t old = k2_add(S, x);
-                acc += __ldg(P.gfix + old);
-                maxold = max(maxold, old);
+                if (olds) {
+                    olds[k] |= old << (16 * hlf);
+                } else {
+                    acc += __ldg(P.gfix + old);
+                    maxold = max(maxold, old);
+                }
                 if (MASKED) ++cnt;
             } else {
                 S.hist[x >> 1] = 0u;
@@ -83,16 +92,17 @@ __device__ __forceinline__ void k2_vec(K2Smem& S, const Params& P, const uint4& 
 }
 
 template <int PHASE, bool MASKED>
-__device__ __forceinline__ void k2_walk(K2Smem& S, const Params& P, const Tile& T, int gt,
+__device__ __forceinline__ void k2_walk(K2Smem& S, const Params& P, const Tile& T, int gt, int gthreads,
                                         const uint4* vreg, const uint2* mreg, uint32_t& cnt,
-                                        uint32_t& maxold, unsigned long long& acc) {
+                                        uint32_t& maxold, unsigned long long& acc, uint32_t (*olds)[4] = nullptr) {
     const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
     const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
     const int nfull = T.n >> 3, rem = T.n & 7;
 #pragma unroll
     for (int i = 0; i < kK2Vec; ++i)
-        if (gt + i * kGroupThreads < nfull) k2_vec<PHASE, MASKED>(S, P, vreg[i], mreg[i], cnt, maxold, acc);
-    for (int idx = gt + kK2Vec * kGroupThreads; idx < nfull; idx += kGroupThreads) {
+        if (gt + i * gthreads < nfull)
+            k2_vec<PHASE, MASKED>(S, P, vreg[i], mreg[i], cnt, maxold, acc, (PHASE == 0 && olds) ? olds[i] : nullptr);
+    for (int idx = gt + kK2Vec * gthreads; idx < nfull; idx += gthreads) {
         const uint4 v = ld_reuse(px4 + idx);
         uint2 m = make_uint2(0u, 0u);
         if (MASKED) m = __ldg(mk2 + idx);
@@ -115,8 +125,8 @@ __device__ __forceinline__ void k2_walk(K2Smem& S, const Params& P, const Tile& 
 }
 
 template <bool MASKED>
-__device__ __forceinline__ void k2_mark_walk(uint32_t* coarse, const Tile& T, int gt, const uint4* vreg,
-                                             const uint2* mreg) {
+__device__ __forceinline__ void k2_mark_walk(uint32_t* coarse, const Tile& T, int gt, int gthreads,
+                                             const uint4* vreg, const uint2* mreg) {
     const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
     const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
     const int nfull = T.n >> 3, rem = T.n & 7;
@@ -124,11 +134,11 @@ __device__ __forceinline__ void k2_mark_walk(uint32_t* coarse, const Tile& T, in
     bool any = !MASKED;
 #pragma unroll
     for (int i = 0; i < kK2Vec; ++i)
-        if (gt + i * kGroupThreads < nfull) {
+        if (gt + i * gthreads < nfull) {
             k2_range<MASKED>(vreg[i], mreg[i], mn2, mx2);
             if (MASKED) any |= (mreg[i].x | mreg[i].y) != 0u;
         }
-    for (int idx = gt + kK2Vec * kGroupThreads; idx < nfull; idx += kGroupThreads) {
+    for (int idx = gt + kK2Vec * gthreads; idx < nfull; idx += gthreads) {
         const uint4 v = ld_reuse(px4 + idx);
         uint2 m = make_uint2(0u, 0u);
         if (MASKED) { m = __ldg(mk2 + idx); any |= (m.x | m.y) != 0u; }
@@ -212,32 +222,35 @@ __device__ __forceinline__ void k2_percentiles(K2Smem& S, const uint32_t* coarse
 }
 
 template <bool MASKED>
-__global__ void __launch_bounds__(kPingPongThreads, 1) k2_order_entropy_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_constant__ Params P, int ng) {
     extern __shared__ __align__(16) unsigned char k2_smem_raw[];
     K2Smem& S = *reinterpret_cast<K2Smem*>(k2_smem_raw);
-    const int tid = threadIdx.x, g = tid / kGroupThreads, gt = tid % kGroupThreads;
-    const int lane = tid & 31, gw = gt >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    Ring R;
+    ring_init(R, S.tokens, ng);
+    const int g = R.g, gt = R.gt, gw = R.gw, gthreads = R.gthreads;
     K2Group& G = S.grp[g];
 
-    for (int k = tid; k < 32768; k += kPingPongThreads) S.hist[k] = 0u;
+    for (int k = tid; k < 32768; k += blockDim.x) S.hist[k] = 0u;
     if (gt < 32) G.coarse[gt] = 0u;
-    if (gt == 0) G.constant = 0;
+    if (gt == 0) { G.constant = 0; G.cnt = 0u; G.acc = 0ull; }
     __syncthreads();
-    if (g == 1) table_release(1);                          // the table starts out free for group 0
 
     const long long first = blockIdx.x;
     const long long mine = first < P.n_tiles ? (P.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
-    const long long n_iter = (mine + 1) / 2;
+    const long long n_iter = (mine + ng - 1) / ng;
     TileWalk walk;
-    walk.init(P, first + (long long)g * gridDim.x < P.n_tiles ? first + (long long)g * gridDim.x : 0, 2ll * gridDim.x);
+    walk.init(P, first + (long long)g * gridDim.x < P.n_tiles ? first + (long long)g * gridDim.x : 0,
+              (long long)ng * gridDim.x);
     for (long long it = 0; it < n_iter; ++it, walk.next()) {
-        const long long k = 2 * it + g;
+        const long long k = (long long)ng * it + g;
         const bool active = k < mine;
         Tile T;
         double* o = nullptr;
         uint4 vreg[kK2Vec];
         uint2 mreg[kK2Vec];
         uint32_t cnt = 0, maxold = 0;
+        uint32_t olds[kK2Vec][4];
         unsigned long long acc = 0ull;
         if (active) {
             T = resolve_tile_rs(P, walk.row, walk.slot);
@@ -247,52 +260,62 @@ __global__ void __launch_bounds__(kPingPongThreads, 1) k2_order_entropy_kernel(c
             const int nfull = T.n >> 3;
 #pragma unroll
             for (int i = 0; i < kK2Vec; ++i) {
-                const int idx = gt + i * kGroupThreads;
+                const int idx = gt + i * gthreads;
                 mreg[i] = make_uint2(0u, 0u);
                 if (idx < nfull) {
                     vreg[i] = ld_stream(px4 + idx);
                     if (MASKED) mreg[i] = __ldg(mk2 + idx);
                 }
             }
-            k2_mark_walk<MASKED>(G.coarse, T, gt, vreg, mreg);   // table-free
+            k2_mark_walk<MASKED>(G.coarse, T, gt, gthreads, vreg, mreg);   // table-free
         }
-        table_acquire(g);                                  // ---- table owned by this group ----
+        ring_acquire(R);                                   // ---- table owned by this group ----
         int n = 0;
         if (active) {
-            k2_walk<0, MASKED>(S, P, T, gt, vreg, mreg, cnt, maxold, acc);
+            k2_walk<0, MASKED>(S, P, T, gt, gthreads, vreg, mreg, cnt, maxold, acc, olds);
             if (MASKED) {
                 cnt = __reduce_add_sync(0xffffffffu, cnt);
-                if (lane == 0) G.wcnt[gw] = cnt;
+                if (lane == 0 && cnt) atomicAdd(&G.cnt, cnt);
             }
-            group_sync(g);                                 // histogram complete
-            n = T.n;
-            if (MASKED) n = (int)__reduce_add_sync(0xffffffffu, lane < kGroupWarps ? G.wcnt[lane] : 0u);
-            if (n > 0 && (int)maxold + 1 == n) G.constant = 1;   // one value only: entropy is exactly 0
+            ring_group_sync(R);                            // histogram complete
+            n = MASKED ? (int)G.cnt : T.n;
             if (gw == 0 && n > 0) k2_percentiles(S, G.coarse, G.vals, P, n, o);
-            group_sync(g);                                 // percentile walk done
-            k2_walk<2, MASKED>(S, P, T, gt, vreg, mreg, cnt, maxold, acc);
+            ring_group_sync(R);                            // percentile walk done, n read by everyone
+            k2_walk<2, MASKED>(S, P, T, gt, gthreads, vreg, mreg, cnt, maxold, acc);
             if (gt < 32) G.coarse[gt] = 0u;
+            if (gt == 0) G.cnt = 0u;
         }
-        if (!(g == 1 && it == n_iter - 1)) table_release(g);   // ---- hand the table over ----
+        ring_release(R);                                   // ---- hand the table to the next group ----
         if (active) {
-            acc = warp_sum(acc);
-            if (lane == 0) G.wpart[gw] = acc;
-            group_sync(g);
+            // entropy terms of the register-resident pixels: G[old], looked up off the critical path
+            const int nfull = T.n >> 3;
+#pragma unroll
+            for (int i = 0; i < kK2Vec; ++i)
+                if (gt + i * gthreads < nfull) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t o2 = olds[i][q];
+                        acc += __ldg(P.gfix + (o2 & 0xffffu));
+                        acc += __ldg(P.gfix + (o2 >> 16));
+                        maxold = max(maxold, max(o2 & 0xffffu, o2 >> 16));
+                    }
+                }
+            if (n > 0 && (int)maxold + 1 == n) G.constant = 1;   // one value only: entropy is exactly 0
+            acc = warp_sum_redux(acc);
+            if (lane == 0) atomicAdd(&G.acc, acc);
+            ring_group_sync(R);
             if (gt == 0) {
                 if (n > 0) {
-                    unsigned long long tot = 0ull;
-#pragma unroll
-                    for (int w = 0; w < kGroupWarps; ++w) tot += G.wpart[w];
-                    // sum_values c*log2(c) = tot * 2^-42 ; H = log2 n - that / n
-                    const double H = __ldg(P.log2tab + n) - ((double)tot * 2.2737367544323206e-13) / (double)n;
+                    // sum_values c*log2(c) = acc * 2^-42 ; H = log2 n - that / n
+                    const double H = __ldg(P.log2tab + n) - ((double)G.acc * 2.2737367544323206e-13) / (double)n;
                     o[16] = G.constant ? 0.0 : H;
-                    G.constant = 0;
                 } else {
                     const double nan = qnan();
 #pragma unroll
                     for (int q = 1; q <= 9; ++q) o[q] = nan;
                     o[16] = nan;
                 }
+                G.constant = 0; G.acc = 0ull;
             }
         }
     }

@@ -19,8 +19,9 @@ namespace imfeat {
 
 constexpr int kK4Threads = 256;
 constexpr int kK4Warps = kK4Threads / 32;
-constexpr int kK4FastDim = 256;
-constexpr int kK4FastWords = kK4FastDim * (kK4FastDim / 32);
+constexpr int kK4FastDim = 256;        // fast path: h, w <= 256 and h*w <= kK4FastPixels
+constexpr int kK4FastPixels = 16384;
+constexpr int kK4FastWords = 1024;     // >= h * ceil(w/32) under the limits above (<= 768)
 constexpr int kK4NInt = 22;   // integer partials per warp
 
 struct K4Smem {
@@ -28,7 +29,11 @@ struct K4Smem {
     int wbox[kK4Warps][4];
     double wdbl[kK4Warps][7];
     union {
-        struct { uint32_t mrow[kK4FastWords]; uint32_t brow[kK4FastWords]; } fast;
+        struct {
+            uint32_t mrow[kK4FastWords]; uint32_t brow[kK4FastWords];
+            uint4 px16[kK4FastPixels / 8];      // the tile, staged with 128-bit loads
+            uint2 m8[kK4FastPixels / 8];        // its mask bytes
+        } fast;
         struct { uint8_t m8[kMaxPixels + 16]; uint8_t b8[kMaxPixels + 16]; } slow;
     } u;
 };
@@ -126,10 +131,23 @@ __global__ void __launch_bounds__(kK4Threads) k4_shape_kernel(const __grid_const
         // a: 0 area 1 sr 2 sc 3 srr 4 scc 5 src 6 n1 7 n2 8 n3 | 9.. raw moments M00 M10 M01 M20 M11
         //    M02 M30 M21 M12 M03 (fast path) or M00 M10 M01 (slow path)
         int rmin = 1 << 30, rmax = -1, cmin = 1 << 30, cmax = -1;
-        const bool fast = h <= kK4FastDim && w <= kK4FastDim;
+        const bool fast = h <= kK4FastDim && w <= kK4FastDim && n <= kK4FastPixels;
 
         if (fast) {
             const int Pw = (w + 31) >> 5;                  // mask words per row
+            // ---- stage the tile (and its mask) in shared memory: all loads of a thread in flight ----
+            {
+                const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
+                const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
+                const int nv = (n + 7) >> 3;
+                for (int i = tid; i < nv; i += kK4Threads) {
+                    if (want_mom) S.u.fast.px16[i] = ld_stream(px4 + i);
+                    if (MASKED) S.u.fast.m8[i] = __ldg(mk2 + i);
+                }
+            }
+            __syncthreads();
+            const uint16_t* spx = reinterpret_cast<const uint16_t*>(S.u.fast.px16);
+            const uint8_t* smk = reinterpret_cast<const uint8_t*>(S.u.fast.m8);
             // ---- pass A: warps over rows, lanes over columns.  Row sums are accumulated per lane
             //      for one 32-column block at a time and folded with the (lane-constant) column
             //      index afterwards: M_pq = sum_c c^q * (sum_r r^p * I[r][c]) ----
@@ -148,8 +166,8 @@ __global__ void __launch_bounds__(kK4Threads) k4_shape_kernel(const __grid_const
                         const int ru = r + u * kK4Warps;
                         const int i = ru * w + c;
                         const bool ok = inb && ru < h;
-                        mk[u] = ok ? (MASKED ? (uint32_t)T.mk[i] : 1u) : 0u;
-                        px[u] = (ok && want_mom) ? (uint32_t)T.px[i] : 0u;
+                        mk[u] = ok ? (MASKED ? (uint32_t)smk[i] : 1u) : 0u;
+                        px[u] = (ok && want_mom) ? (uint32_t)spx[i] : 0u;
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
