@@ -25,13 +25,18 @@ struct K2Group {
     int vals[18];
     uint32_t cnt;            // masked pixel count (integer atomics)
     int constant;
-    unsigned long long acc;  // sum of G[old] in 2^-42 fixed point (integer atomics)
+    unsigned long long wacc[16];   // per-warp sums of G[old] in 2^-42 fixed point
 };
+constexpr int kK2GfixSmem = 4096;  // entropy-table entries mirrored in shared memory
 struct K2Smem {
     uint32_t hist[32768];
+    unsigned long long gfix[kK2GfixSmem];
     unsigned long long tokens[8];
     K2Group grp[8];
 };
+__device__ __forceinline__ unsigned long long k2_gfix(const K2Smem& S, const Params& P, uint32_t old) {
+    return old < (uint32_t)kK2GfixSmem ? S.gfix[old] : __ldg(P.gfix + old);
+}
 
 // returns the count of x BEFORE this increment
 __device__ __forceinline__ uint32_t k2_add(K2Smem& S, uint32_t x) {
@@ -80,7 +85,7 @@ __device__ __forceinline__ void k2_vec(K2Smem& S, const Params& P, const uint4& 
                 if (olds) {
                     olds[k] |= old << (16 * hlf);
                 } else {
-                    acc += __ldg(P.gfix + old);
+                    acc += k2_gfix(S, P, old);
                     maxold = max(maxold, old);
                 }
                 if (MASKED) ++cnt;
@@ -114,7 +119,7 @@ __device__ __forceinline__ void k2_walk(K2Smem& S, const Params& P, const Tile& 
             const uint32_t x = T.px[i];
             if (PHASE == 0) {
                 const uint32_t old = k2_add(S, x);
-                acc += __ldg(P.gfix + old);
+                acc += k2_gfix(S, P, old);
                 maxold = max(maxold, old);
                 if (MASKED) ++cnt;
             } else {
@@ -233,7 +238,8 @@ __global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_
 
     for (int k = tid; k < 32768; k += blockDim.x) S.hist[k] = 0u;
     if (gt < 32) G.coarse[gt] = 0u;
-    if (gt == 0) { G.constant = 0; G.cnt = 0u; G.acc = 0ull; }
+    if (gt == 0) { G.constant = 0; G.cnt = 0u; }
+    for (int k = tid; k < kK2GfixSmem; k += blockDim.x) S.gfix[k] = __ldg(P.gfix + k);
     __syncthreads();
 
     const long long first = blockIdx.x;
@@ -242,31 +248,37 @@ __global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_
     TileWalk walk;
     walk.init(P, first + (long long)g * gridDim.x < P.n_tiles ? first + (long long)g * gridDim.x : 0,
               (long long)ng * gridDim.x);
-    for (long long it = 0; it < n_iter; ++it, walk.next()) {
-        const long long k = (long long)ng * it + g;
-        const bool active = k < mine;
-        Tile T;
-        double* o = nullptr;
-        uint4 vreg[kK2Vec];
-        uint2 mreg[kK2Vec];
+
+    // The pixels of a tile live in registers; the next tile's loads are issued right after the
+    // table has been handed over, so HBM latency hides behind the current tile's epilogue and the
+    // other groups' table phases.
+    uint4 vreg[kK2Vec];
+    uint2 mreg[kK2Vec];
+    Tile T;
+    bool active = g < mine;
+    auto fetch = [&](const Tile& Tn) {
+        const uint4* px4 = reinterpret_cast<const uint4*>(Tn.px);
+        const uint2* mk2 = reinterpret_cast<const uint2*>(Tn.mk);
+        const int nfull = Tn.n >> 3;
+#pragma unroll
+        for (int i = 0; i < kK2Vec; ++i) {
+            const int idx = gt + i * gthreads;
+            mreg[i] = make_uint2(0u, 0u);
+            if (idx < nfull) {
+                vreg[i] = ld_stream(px4 + idx);
+                if (MASKED) mreg[i] = __ldg(mk2 + idx);
+            }
+        }
+    };
+    if (active) { T = resolve_tile_rs(P, walk.row, walk.slot); fetch(T); }
+
+    for (long long it = 0; it < n_iter; ++it) {
         uint32_t cnt = 0, maxold = 0;
         uint32_t olds[kK2Vec][4];
         unsigned long long acc = 0ull;
+        double* o = nullptr;
         if (active) {
-            T = resolve_tile_rs(P, walk.row, walk.slot);
             o = T.out_row + P.col_basic + kNBasic * T.slot;
-            const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
-            const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
-            const int nfull = T.n >> 3;
-#pragma unroll
-            for (int i = 0; i < kK2Vec; ++i) {
-                const int idx = gt + i * gthreads;
-                mreg[i] = make_uint2(0u, 0u);
-                if (idx < nfull) {
-                    vreg[i] = ld_stream(px4 + idx);
-                    if (MASKED) mreg[i] = __ldg(mk2 + idx);
-                }
-            }
             k2_mark_walk<MASKED>(G.coarse, T, gt, gthreads, vreg, mreg);   // table-free
         }
         ring_acquire(R);                                   // ---- table owned by this group ----
@@ -286,28 +298,38 @@ __global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_
             if (gt == 0) G.cnt = 0u;
         }
         ring_release(R);                                   // ---- hand the table to the next group ----
-        if (active) {
+
+        // prefetch the next tile of this group (the pixel registers are free again)
+        const Tile Tcur = T;
+        const bool was_active = active;
+        walk.next();
+        active = (long long)ng * (it + 1) + g < mine;
+        if (active) { T = resolve_tile_rs(P, walk.row, walk.slot); fetch(T); }
+
+        if (was_active) {
             // entropy terms of the register-resident pixels: G[old], looked up off the critical path
-            const int nfull = T.n >> 3;
+            const int nfull = Tcur.n >> 3;
 #pragma unroll
             for (int i = 0; i < kK2Vec; ++i)
                 if (gt + i * gthreads < nfull) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint32_t o2 = olds[i][q];
-                        acc += __ldg(P.gfix + (o2 & 0xffffu));
-                        acc += __ldg(P.gfix + (o2 >> 16));
+                        acc += k2_gfix(S, P, o2 & 0xffffu);
+                        acc += k2_gfix(S, P, o2 >> 16);
                         maxold = max(maxold, max(o2 & 0xffffu, o2 >> 16));
                     }
                 }
             if (n > 0 && (int)maxold + 1 == n) G.constant = 1;   // one value only: entropy is exactly 0
             acc = warp_sum_redux(acc);
-            if (lane == 0) atomicAdd(&G.acc, acc);
+            if (lane == 0) G.wacc[gw] = acc;
             ring_group_sync(R);
             if (gt == 0) {
                 if (n > 0) {
                     // sum_values c*log2(c) = acc * 2^-42 ; H = log2 n - that / n
-                    const double H = __ldg(P.log2tab + n) - ((double)G.acc * 2.2737367544323206e-13) / (double)n;
+                    unsigned long long tot = 0ull;
+                    for (int w = 0; w < R.gwarps; ++w) tot += G.wacc[w];
+                    const double H = __ldg(P.log2tab + n) - ((double)tot * 2.2737367544323206e-13) / (double)n;
                     o[16] = G.constant ? 0.0 : H;
                 } else {
                     const double nan = qnan();
@@ -315,7 +337,7 @@ __global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_
                     for (int q = 1; q <= 9; ++q) o[q] = nan;
                     o[16] = nan;
                 }
-                G.constant = 0; G.acc = 0ull;
+                G.constant = 0;
             }
         }
     }

@@ -27,7 +27,7 @@ constexpr int kK3Cache = 4;     // pair groups (4 pairs each) per thread cached 
 
 // Shared-memory layout (dynamic): [hist 128 KB][homtab 2 KB][tokens][per-group: K3GroupHdr, q8, mbits]
 struct K3GroupHdr {
-    unsigned long long homfix[kMaxAngles];     // sum 1/(1+d^2) in 2^-40 fixed point, per direction
+    unsigned long long whom[kMaxAngles][16];   // per-warp sums of 1/(1+d^2) in 2^-40 fixed point
     uint32_t acc[kMaxAngles][8];               // si sj sii sjj sij sd sold m, per direction
     uint32_t wmax[32];
 };
@@ -193,7 +193,6 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
     if (tid < 256) S.homtab[tid] = 1.0 / (1.0 + (double)(tid * tid));
     if (tid < 2) S.dummy[tid] = 0u;
     if (gt < kMaxAngles * 8) H.acc[gt >> 3][gt & 7] = 0u;
-    if (gt < kMaxAngles) H.homfix[gt] = 0ull;
     __syncthreads();
 
     const long long first = blockIdx.x;
@@ -299,7 +298,7 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < 6; ++k) atomicAdd(&H.acc[a][k], red[k]);
                     atomicAdd(&H.acc[a][7], mm);
-                    atomicAdd(&H.homfix[a], hf);
+                    H.whom[a][gw] = hf;
                 }
             }
             ring_acquire(R);                               // ---- table owned by this group ----
@@ -348,7 +347,9 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
                 const K3Geom Ge = k3_geom(T.h, T.w, P.dr[a], P.dc[a]);
                 const long long D = MASKED ? 0ll : 4ll * Ge.nrows * Ge.gpr - M;
                 const unsigned long long sold_true = (unsigned long long)s[6] - (unsigned long long)(D * (D - 1) / 2);
-                const unsigned long long hom_true = H.homfix[a] - ((unsigned long long)D << 40);
+                unsigned long long hom_sum = 0ull;
+                for (int w = 0; w < R.gwarps; ++w) hom_sum += H.whom[a][w];
+                const unsigned long long hom_true = hom_sum - ((unsigned long long)D << 40);
                 double* o = T.out_row + P.col_glcm + (T.slot * P.n_angles + a) * kNGlcm;
                 if (M == 0) {
                     o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 0.0; o[4] = 0.0; o[5] = 1.0;
@@ -370,7 +371,6 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
             }
             ring_group_sync(R);                            // accumulators consumed
             if (gt < kMaxAngles * 8) H.acc[gt >> 3][gt & 7] = 0u;
-            if (gt < kMaxAngles) H.homfix[gt] = 0ull;
         }
     }
 }
