@@ -142,6 +142,7 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k4_shape_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k4_shape_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_moments_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_bps[0], k1_moments_kernel<false>, 256, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_bps[1], k1_moments_kernel<true>, 256, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4_bps[0], k4_shape_kernel<false>, kK4Threads, sizeof(K4Smem));
@@ -301,7 +302,17 @@ static int launch_all(imfeat_ctx* ctx, const Params& P, const imfeat_opts* o, cu
     if (o->want_basic) {
         const long long res1 = sm * (ctx->k1_bps[masked] > 0 ? ctx->k1_bps[masked] : 1);   // one resident wave
         const int g1 = (int)((P.n_tiles + 7) / 8 < res1 ? (P.n_tiles + 7) / 8 : res1);
-        if (masked) k1_moments_kernel<true><<<g1, 256, 0, st>>>(P);
+        const char* k1env = getenv("IMFEAT_K1_TMA");
+        const bool use_tma = !masked && k1env && atoi(k1env) == 1;   // measured: no faster than the direct path
+        if (use_tma) {
+            // shared-memory ring of whole tiles filled by cp.async.bulk; one persistent CTA per SM
+            const int stage_bytes = ((P.hs * P.ws * 2 + 127) & ~127);
+            int n_stages = (200 * 1024) / stage_bytes;
+            if (n_stages > 32) n_stages = 32;
+            const size_t smem = (size_t)n_stages * stage_bytes + 16 * (size_t)n_stages;
+            const int gt = (int)(P.n_tiles < sm ? P.n_tiles : sm);
+            k1_moments_tma_kernel<<<gt, kK1TmaThreads, smem, st>>>(P, n_stages, stage_bytes);
+        } else if (masked) k1_moments_kernel<true><<<g1, 256, 0, st>>>(P);
         else k1_moments_kernel<false><<<g1, 256, 0, st>>>(P);
         IMFEAT_MARK(0)
         const int g2 = (int)(P.n_tiles < sm ? P.n_tiles : sm);

@@ -216,3 +216,140 @@ __global__ void __launch_bounds__(256) k1_moments_kernel(const __grid_constant__
 }
 
 }  // namespace imfeat
+
+// -------------------------------------------------------------------------------------------------
+// K1, bulk-copy variant (unmasked tiles, opt-in with IMFEAT_K1_TMA=1): a producer thread streams whole
+// tiles into a shared-memory ring with cp.async.bulk (the 1-D TMA path, UBLKCP) completing on
+// mbarriers; each consumer warp owns one tile at a time and reads it with conflict-free 128-bit
+// shared loads.  Measured on B200 it is no faster than the direct-load kernel above (0.316 ms vs
+// 0.296 ms per 10,000 objects): K1 is bound by instruction issue / the FP64 pipe, not by HBM
+// latency, so the ring only removes stalls that occupancy already hides.
+// -------------------------------------------------------------------------------------------------
+namespace imfeat {
+
+constexpr int kK1TmaConsumers = 16;                 // consumer warps per CTA
+constexpr int kK1TmaThreads = 32 * (kK1TmaConsumers + 1);
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kK1TmaThreads, 1)
+k1_moments_tma_kernel(const __grid_constant__ Params P, int n_stages, int stage_bytes) {
+    extern __shared__ __align__(128) unsigned char k1_smem[];
+    // layout: [stages][full barriers][empty barriers]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(k1_smem + (size_t)n_stages * stage_bytes);
+    const uint32_t stage0 = smem_addr(k1_smem);
+    const uint32_t full0 = smem_addr(bars), empty0 = smem_addr(bars + n_stages);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0)
+        for (int s = 0; s < n_stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const long long first = blockIdx.x;
+    const long long mine = first < P.n_tiles ? (P.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == kK1TmaConsumers) {
+        // ---- producer: one lane issues the bulk copies ----
+        if (lane == 0) {
+            TileWalk walk;
+            walk.init(P, first < P.n_tiles ? first : 0, gridDim.x);
+            for (long long k = 0; k < mine; ++k, walk.next()) {
+                const int s = (int)(k % n_stages);
+                const uint32_t ph = (uint32_t)((k / n_stages) & 1);
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);                       // slot free (first round passes)
+                const Tile T = resolve_tile_rs(P, walk.row, walk.slot);
+                const uint32_t bytes = ((uint32_t)T.n * 2u + 15u) & ~15u;  // padding inside the plane stride
+                mbar_expect_tx(full0 + 8 * s, bytes);
+                bulk_g2s(stage0 + (uint32_t)s * (uint32_t)stage_bytes, T.px, bytes, full0 + 8 * s);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: warp w takes tiles w, w + CW, ... of this CTA ----
+    TileWalk walk;
+    walk.init(P, first + (long long)warp * gridDim.x < P.n_tiles ? first + (long long)warp * gridDim.x : 0,
+              (long long)kK1TmaConsumers * gridDim.x);
+    for (long long k = warp; k < mine; k += kK1TmaConsumers, walk.next()) {
+        const int s = (int)(k % n_stages);
+        const uint32_t ph = (uint32_t)((k / n_stages) & 1);
+        const Tile T = resolve_tile_rs(P, walk.row, walk.slot);
+        const int nfull = T.n >> 3, rem = T.n & 7;
+        const uint4* px4 = reinterpret_cast<const uint4*>(k1_smem + (size_t)s * stage_bytes);
+        const uint16_t* px1 = reinterpret_cast<const uint16_t*>(px4);
+        mbar_wait(full0 + 8 * s, ph);                                     // tile landed
+
+        uint32_t xt = 0;
+        const bool tail_ok = lane < rem;
+        if (tail_ok) xt = px1[nfull * 8 + lane];
+        uint32_t ssum = tail_ok ? xt : 0u, scnt = tail_ok ? 1u : 0u;
+        {
+            const int s0 = nfull > 32 ? (nfull >> 1) - 16 : 0;
+            const int idx = s0 + lane;
+            if (idx < nfull) {
+                const uint4 v = px4[idx];
+                scnt += 8;
+                ssum = __dp2a_lo(v.x, 0x0101u, ssum); ssum = __dp2a_lo(v.y, 0x0101u, ssum);
+                ssum = __dp2a_lo(v.z, 0x0101u, ssum); ssum = __dp2a_lo(v.w, 0x0101u, ssum);
+            }
+        }
+        ssum = __reduce_add_sync(0xffffffffu, ssum);
+        scnt = __reduce_add_sync(0xffffffffu, scnt);
+        const long long p = scnt ? (long long)((ssum + (scnt >> 1)) / scnt) : 0;
+        const unsigned long long c64 = (0x43300000ull << 32) | (unsigned long long)((1u << 20) - (uint32_t)p);
+
+        K1State st;
+        st.mn2 = 0xffffffffu; st.mx2 = 0u; st.sum = 0u; st.cnt = 0u;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) st.S[q] = 0.0;
+        const uint2 nomask = make_uint2(0u, 0u);
+        int idx = lane;
+        for (; idx + 32 < nfull; idx += 64) {
+            const uint4 v0 = px4[idx], v1 = px4[idx + 32];
+            k1_vec<false>(v0, nomask, c64, st);
+            k1_vec<false>(v1, nomask, c64, st);
+        }
+        for (; idx < nfull; idx += 32) k1_vec<false>(px4[idx], nomask, c64, st);
+        if (tail_ok) {
+            st.mn2 = __vminu2(st.mn2, xt | 0xffff0000u);
+            st.mx2 = __vmaxu2(st.mx2, xt);
+            st.sum += xt;
+            k1_px(xt, c64, st.S[0], st.S[1], st.S[2]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * s);                       // stage can be refilled
+
+        const uint32_t total = __reduce_add_sync(0xffffffffu, st.sum);
+        const uint32_t vmin = __reduce_min_sync(0xffffffffu, min(st.mn2 & 0xffffu, st.mn2 >> 16));
+        const uint32_t vmax = __reduce_max_sync(0xffffffffu, max(st.mx2 & 0xffffu, st.mx2 >> 16));
+        const double S2 = warp_sum(st.S[0] + st.S[3]);
+        const double S3 = warp_sum(st.S[1] + st.S[4]);
+        const double S4 = warp_sum(st.S[2] + st.S[5]);
+        if (lane == 0) k1_epilogue(P, T, (uint32_t)T.n, vmin, vmax, total, p, S2, S3, S4);
+    }
+}
+
+}  // namespace imfeat
