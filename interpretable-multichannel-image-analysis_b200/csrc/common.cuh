@@ -163,9 +163,9 @@ __device__ __forceinline__ void ring_acquire(Ring& R) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@!p bra WAIT_%=;\n"
-        "}\n" ::"r"(R.tok_mine), "r"(R.parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware
+        "}\n" ::"r"(R.tok_mine), "r"(R.parity)
         : "memory");
     R.parity ^= 1u;
 }

@@ -198,10 +198,13 @@ static int k3_groups(int max_pixels) {
     return want;
 }
 
-static int k2_groups() {
+// K2: measured on B200 (10,000 64x64x12 objects): unmasked 1.59 ms with 4 groups vs 1.84 ms with 2;
+// masked 2.60 ms vs 2.51 ms.
+static int k2_groups(bool masked) {
     const char* env = getenv("IMFEAT_K2_GROUPS");
-    const int want = env ? atoi(env) : 2;
-    return (want == 2 || want == 4 || want == 8) ? want : 2;
+    const int def = masked ? 2 : 4;
+    const int want = env ? atoi(env) : def;
+    return (want == 2 || want == 4 || want == 8) ? want : def;
 }
 
 // C round(): half away from zero, as skimage's _glcm_loop uses for the pixel offsets.
@@ -316,7 +319,7 @@ static int launch_all(imfeat_ctx* ctx, const Params& P, const imfeat_opts* o, cu
         else k1_moments_kernel<false><<<g1, 256, 0, st>>>(P);
         IMFEAT_MARK(0)
         const int g2 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
-        const int ng2 = k2_groups();
+        const int ng2 = k2_groups(masked);
         if (masked) k2_order_entropy_kernel<true><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2);
         else k2_order_entropy_kernel<false><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2);
         IMFEAT_MARK(1)

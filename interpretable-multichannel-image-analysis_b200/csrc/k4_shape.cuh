@@ -114,7 +114,7 @@ __device__ __forceinline__ void k4_moment_epilogue(const Params& P, const Tile& 
 }
 
 template <bool MASKED>
-__global__ void __launch_bounds__(kK4Threads) k4_shape_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(kK4Threads, 3) k4_shape_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) unsigned char k4_smem_raw[];
     K4Smem& S = *reinterpret_cast<K4Smem*>(k4_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
