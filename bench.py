@@ -259,6 +259,13 @@ def run_b200(args):
         per_kernel.append({"kernel": names[k], "ms_per_launch": avg_ms, "share": kms[k] / sum(kms),
                            "achieved_gbs": b / (avg_ms * 1e-3) / 1e9, "frac": b / (avg_ms * 1e-3) / 1e9 / peak})
     dom = max(per_kernel, key=lambda d: d["ms_per_launch"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if n_obj == 10000 and os.path.exists(tpath):          # measured for exactly this workload
+        try:
+            traffic = json.load(open(tpath)).get(dom["kernel"])
+        except Exception:
+            traffic = None
     nb_feats = [7, 10, 6]
     nb_kernels = []
     for k in range(3):
@@ -288,7 +295,10 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak,
-                     "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                     "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read+write per launch)" if traffic else None,
+                     "algorithmic_bytes": n_obj * algorithmic_bytes_per_object(HS, WS, C, 1, feats[names.index(dom["kernel"])]),
+                     "bound_note": "HBM is the roofline asked for; ncu shows this kernel limited by instruction issue (65% issue-active), see profiles/",
                      "note": "algorithmic bytes = N*(2hwC + 1*hwC + 8*F_k*C), F_k = this kernel's features"},
         "roofline_kernels": per_kernel,
         "roofline_path": {"achieved": b_path / (ms_step * 1e-3) / 1e9, "frac": b_path / (ms_step * 1e-3) / 1e9 / peak},

@@ -278,3 +278,98 @@ def test_full_size_properties(torch_mod):
         img = np.stack([synth.synth_plane(0, int(i), ch, 64, 64)[0] for ch in range(C)], axis=2)[None]
         want = c_oracle.table(_planar(img), glcm=True, n_angles=4)
         compare_tables(t[i:i + 1], want, cols, label="sample %d" % i)
+
+
+def test_custom_percentiles_and_distance(torch_mod):
+    """Options away from the notebook literals: arbitrary np.percentile arguments (including 0, 50
+    and 100) and another GLCM distance, against numpy / the restated greycomatrix directly."""
+    rng = np.random.default_rng(21)
+    d = parity_distributions(rng, 40, 56)
+    names = sorted(d)
+    img = np.stack([d[k] for k in names], axis=2)[None]
+    qs = (0.0, 1.0, 12.5, 25.0, 50.0, 75.0, 90.0, 99.9, 100.0)
+    got = imf.extract_features(img, glcm=True, percentiles=qs, distance=2, four_directions=True)
+    cols = imf.feature_columns(len(names), n_angles=4)
+    for c, k in enumerate(names):
+        plane = d[k]
+        for j, q in enumerate(qs):
+            assert got[0, cols.index("percentile%d0_intensity_Ch%d" % (j + 1, c + 1))] == np.percentile(plane, q), (k, q)
+        qz = orc.quantise(plane)
+        P = orc.greycomatrix(qz, [2], list(orc.ANGLES4), levels=256)
+        for a, tag in enumerate(orc.ANGLE_TAGS):
+            for prop in orc.GLCM_PROPS:
+                want = float(orc.greycoprops(P[:, :, :, a:a + 1], prop)[0, 0])
+                g = got[0, cols.index("%s%s_Ch%d" % (prop, tag, c + 1))]
+                ok = np.isclose(g, want, rtol=1e-9, atol=1e-9) or (prop == "correlation" and g == 1.0 and abs(want) < 1e-6)
+                assert ok, (k, tag, prop, g, want)
+
+
+@pytest.mark.parametrize("C", [1, 3, 18])
+def test_channel_counts_and_status_bits(C, torch_mod):
+    from imfeat_b200 import synth
+    img, mask = synth.synth_batch_hwc(3, 0, 16, C, 64, 64)
+    mask[5] = 0                                   # object 5: every mask empty
+    img[7, :, :, 0] = 777                         # object 7, channel 0: constant
+    want = c_oracle.table(_planar(img), _planar(mask), glcm=True, n_angles=1)
+    got, status = imf.extract_features(img, mask, return_status=True)
+    compare_tables(got, want, imf.feature_columns(C), label="C=%d" % C)
+    assert status[5] & 1 and status[5] & 2        # empty mask, zero GLCM pairs
+    assert status[7] & 4                          # constant channel
+    assert not (status[0] & 1)
+
+
+def test_host_path_multiple_slabs(torch_mod):
+    """The host entry point pipelines ~64 MiB slabs; 1,500 objects = 3 slabs.  Pageable and pinned
+    inputs, with and without masks, must give the table of the device path bit for bit."""
+    torch = torch_mod
+    ex = imf.get_extractor()
+    n = 1500
+    planes, masks, _ = ex.synth(11, 0, n, 12, 64, 64)
+    dev = ex.extract_planar(planes, None, hs=64, ws=64).cpu().numpy()
+    devm = ex.extract_planar(planes, masks, hs=64, ws=64).cpu().numpy()
+    hwc = planes[:, :, :4096].reshape(n, 12, 64, 64).permute(0, 2, 3, 1).contiguous().cpu()
+    mhwc = masks[:, :, :4096].reshape(n, 12, 64, 64).permute(0, 2, 3, 1).contiguous().cpu()
+    assert np.array_equal(ex.extract_host_hwc(hwc.numpy()), dev, equal_nan=True)
+    assert np.array_equal(ex.extract_host_hwc(hwc.numpy(), mhwc.numpy()), devm, equal_nan=True)
+    pin, mpin = hwc.pin_memory(), mhwc.pin_memory()
+    assert np.array_equal(ex.extract_host_hwc(pin.numpy(), mpin.numpy()), devm, equal_nan=True)
+
+
+def test_ablation_sweep_driver(torch_mod):
+    """channel_ablation_sweep (device-side loop) == column-block operations on the base table."""
+    from imfeat_b200 import ablation, schema
+    ex = imf.get_extractor()
+    C, N = 5, 40
+    planes, masks, _ = ex.synth(8, 0, N, C, 64, 64)
+    base = ex.extract_planar(planes, masks, hs=64, ws=64).cpu().numpy()
+    loco = ablation.channel_ablation_sweep(ex, planes, masks, hs=64, ws=64, mode="loco").cpu().numpy()
+    assert loco.shape == (C, N, ex.row_width(C - 1))
+    for k in range(C):
+        keep = [c for c in range(C) if c != k]
+        for pos, c in enumerate(keep):
+            assert np.array_equal(loco[k][:, schema.channel_column_index(C - 1, pos)],
+                                  base[:, schema.channel_column_index(C, c)], equal_nan=True)
+    perm = ablation.channel_ablation_sweep(ex, planes, masks, hs=64, ws=64, mode="permute", seed=42).cpu().numpy()
+    src = ablation.permutation_sources(N, C, seed=42)
+    for k in range(C):
+        want = base.copy()
+        cidx = schema.channel_column_index(C, k)
+        want[:, cidx] = base[src[k][:, k]][:, cidx]
+        assert np.array_equal(perm[k], want, equal_nan=True)
+
+
+def test_repeatability(torch_mod):
+    """Same inputs, different launches / streams: identical bits (integer accumulation everywhere
+    order could matter)."""
+    torch = torch_mod
+    ex = imf.get_extractor(four_directions=True, shape=True, moments=True)
+    planes, masks, _ = ex.synth(4, 0, 300, 12, 64, 64)
+    a = ex.extract_planar(planes, masks, hs=64, ws=64).clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        b = ex.extract_planar(planes, masks, hs=64, ws=64, stream=s).clone()
+    s.synchronize()
+    c = ex.extract_planar(planes, masks, hs=64, ws=64)
+    torch.cuda.synchronize()
+    assert torch.equal(a.view(torch.int64), b.view(torch.int64))
+    assert torch.equal(a.view(torch.int64), c.view(torch.int64))
