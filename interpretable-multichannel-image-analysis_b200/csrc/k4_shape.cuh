@@ -158,32 +158,25 @@ __global__ void __launch_bounds__(kK4Threads, 3) k4_shape_kernel(const __grid_co
                 const bool inb = c < w;
                 uint32_t cnt = 0, csr = 0, csrr = 0, b0 = 0, b1 = 0;
                 unsigned long long b2 = 0, b3 = 0;
-                int r = warp;
-                for (; r < h; r += kK4Warps * 4) {
-                    uint32_t mk[4], px[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {         // issue the loads of four rows first
-                        const int ru = r + u * kK4Warps;
-                        const int i = ru * w + c;
-                        const bool ok = inb && ru < h;
-                        mk[u] = ok ? (MASKED ? (uint32_t)smk[i] : 1u) : 0u;
-                        px[u] = (ok && want_mom) ? (uint32_t)spx[i] : 0u;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int ru = r + u * kK4Warps;
-                        if (ru >= h) break;                // warp-uniform
-                        const bool m = mk[u] != 0u;
-                        const uint32_t bal = __ballot_sync(0xffffffffu, m);
-                        if (lane == 0) S.u.fast.mrow[ru * Pw + (c0 >> 5)] = bal;
-                        const uint32_t m1 = m ? 1u : 0u, im = m ? px[u] : 0u;
-                        const uint32_t r1 = ru, r2 = ru * ru, r3 = r2 * ru;
-                        cnt += m1; csr += m1 * r1; csrr += m1 * r2;
-                        if (m) { rmin = min(rmin, ru); rmax = max(rmax, ru); }
-                        b0 += im; b1 += im * r1;
-                        b2 += (unsigned long long)im * r2;
-                        b3 += (unsigned long long)im * r3;
-                    }
+                // running pointers: row `warp` of this column block, advanced by kK4Warps rows per step
+                const uint8_t* mp = smk + warp * w + (inb ? c : 0);
+                const uint16_t* pp = spx + warp * w + (inb ? c : 0);
+                uint32_t* mr = S.u.fast.mrow + warp * Pw + (c0 >> 5);
+                const int mstep = kK4Warps * w, wstep = kK4Warps * Pw;
+#pragma unroll 4
+                for (int r = warp; r < h; r += kK4Warps) {
+                    const bool m = inb && (!MASKED || *mp != 0);
+                    const uint32_t pxv = want_mom ? (uint32_t)*pp : 0u;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, m);
+                    if (lane == 0) *mr = bal;
+                    const uint32_t m1 = m ? 1u : 0u, im = m ? pxv : 0u;
+                    const uint32_t r1 = r, r2 = r * r, r3 = r2 * r;
+                    cnt += m1; csr += m1 * r1; csrr += m1 * r2;
+                    rmin = m ? min(rmin, r) : rmin; rmax = m ? max(rmax, r) : rmax;
+                    b0 += im; b1 += im * r1;
+                    b2 += (unsigned long long)im * r2;
+                    b3 += (unsigned long long)im * r3;
+                    mp += mstep; pp += mstep; mr += wstep;
                 }
                 if (cnt) { cmin = min(cmin, c); cmax = max(cmax, c); }
                 const uint32_t c1 = inb ? c : 0, c2 = c1 * c1, c3 = c2 * c1;
