@@ -30,6 +30,7 @@ struct K3GroupHdr {
     unsigned long long whom[kMaxAngles][16];   // per-warp sums of 1/(1+d^2) in 2^-40 fixed point
     uint32_t acc[kMaxAngles][8];               // si sj sii sjj sij sd sold m, per direction
     uint32_t wmax[32];
+    int box[4];                                // mask bounding box: rmin, rmax, cmin, cmax (masked variant)
 };
 struct K3Smem {
     uint32_t hist[32768];
@@ -85,13 +86,16 @@ __device__ __forceinline__ uint32_t k3_mask4(const uint32_t* b, int off) {
 }
 
 struct K3Geom {
-    int nrows, c0, c1, gpr, lg, items, w, doff;
+    int nrows, r0, c0, c1, gpr, lg, items, w, doff;
 };
-__device__ __forceinline__ K3Geom k3_geom(int h, int w, int dr, int dc) {
+// Pairs (r, c) -> (r + dr, c + dc) with both pixels inside the box rows [br0, br1], columns
+// [bc0, bc1] (the whole tile, or the bounding box of the mask: pairs outside it cannot exist).
+__device__ __forceinline__ K3Geom k3_geom(int w, int dr, int dc, int br0, int br1, int bc0, int bc1) {
     K3Geom G;
-    G.nrows = h - dr;                              // dr >= 0 for all supported directions
-    G.c0 = dc < 0 ? -dc : 0;
-    G.c1 = dc < 0 ? w : w - dc;
+    G.r0 = br0;
+    G.nrows = br1 - dr - br0 + 1;                  // dr >= 0 for all supported directions
+    G.c0 = bc0 + (dc < 0 ? -dc : 0);
+    G.c1 = bc1 + 1 - (dc > 0 ? dc : 0);
     G.w = w;
     G.doff = dr * w + dc;
     if (G.nrows <= 0 || G.c1 <= G.c0) { G.items = 0; G.gpr = 0; G.lg = 0; G.nrows = 0; return G; }
@@ -106,7 +110,7 @@ __device__ __forceinline__ K3Geom k3_geom(int h, int w, int dr, int dc) {
 template <bool MASKED>
 __device__ __forceinline__ bool k3_item(const K3Group& Gp, const K3Geom& G, int item, uint32_t& I4,
                                         uint32_t& J4, uint32_t& vm) {
-    const int r = item >> G.lg, cg = item & ((1 << G.lg) - 1);
+    const int r = G.r0 + (item >> G.lg), cg = item & ((1 << G.lg) - 1);
     if (cg >= G.gpr) { vm = 0u; I4 = J4 = 0u; return false; }
     const int c = G.c0 + 4 * cg;
     const int valid = min(4, G.c1 - c);
@@ -192,6 +196,7 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
     for (int k = tid; k < 32768; k += blockDim.x) S.hist[k] = 0u;
     if (tid < 256) S.homtab[tid] = 1.0 / (1.0 + (double)(tid * tid));
     if (tid < 2) S.dummy[tid] = 0u;
+    if (gt == 0) { H.box[0] = 1 << 30; H.box[1] = -1; H.box[2] = 1 << 30; H.box[3] = -1; }
     if (gt < kMaxAngles * 8) H.acc[gt >> 3][gt & 7] = 0u;
     __syncthreads();
 
@@ -214,8 +219,9 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
             const int nfull = T.n >> 3, rem = T.n & 7;
             uint8_t* mbytes = reinterpret_cast<uint8_t*>(Gp.mbits);
 
-            // ---- 1. tile maximum (over the mask when masked); stage the mask bits ----
+            // ---- 1. tile maximum (over the mask when masked); stage the mask bits and their bounding box ----
             uint32_t mx2 = 0u;
+            int brmin = 1 << 30, brmax = -1, bcmin = 1 << 30, bcmax = -1;
             for (int idx = gt; idx < nfull; idx += gthreads) {
                 uint4 v = ld_reuse(px4 + idx);
                 if (MASKED) {
@@ -224,7 +230,18 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
                     // 8 mask bytes -> 8 bits (byte k -> bit k)
                     const uint32_t b0 = ((c0 & 0x01010101u) * 0x01020408u) >> 24;
                     const uint32_t b1 = ((c1 & 0x01010101u) * 0x01020408u) >> 24;
-                    mbytes[idx] = (uint8_t)((b0 & 0xfu) | ((b1 & 0xfu) << 4));
+                    const uint32_t bits8 = (b0 & 0xfu) | ((b1 & 0xfu) << 4);
+                    mbytes[idx] = (uint8_t)bits8;
+                    if (bits8) {
+                        const int p0 = 8 * idx, ra = p0 / T.w, ca = p0 - ra * T.w;
+                        if (ca + 7 < T.w) {                // the 8 pixels lie in one row
+                            brmin = min(brmin, ra); brmax = max(brmax, ra);
+                            bcmin = min(bcmin, ca + __ffs(bits8) - 1); bcmax = max(bcmax, ca + 31 - __clz(bits8));
+                        } else {                           // straddles rows: be conservative
+                            brmin = min(brmin, ra); brmax = max(brmax, (p0 + 7) / T.w);
+                            bcmin = 0; bcmax = T.w - 1;
+                        }
+                    }
                     v.x &= __byte_perm(c0, 0u, 0x1100); v.y &= __byte_perm(c0, 0u, 0x3322);
                     v.z &= __byte_perm(c1, 0u, 0x1100); v.w &= __byte_perm(c1, 0u, 0x3322);
                 }
@@ -235,9 +252,21 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
                 for (int k = 0; k < rem; ++k) {
                     const int i = nfull * 8 + k;
                     const bool ok = !MASKED || T.mk[i] != 0;
-                    if (ok) { bits |= 1u << k; mx2 = __vmaxu2(mx2, (uint32_t)T.px[i]); }
+                    if (ok) {
+                        bits |= 1u << k; mx2 = __vmaxu2(mx2, (uint32_t)T.px[i]);
+                        const int ra = i / T.w, ca = i - ra * T.w;
+                        brmin = min(brmin, ra); brmax = max(brmax, ra); bcmin = min(bcmin, ca); bcmax = max(bcmax, ca);
+                    }
                 }
                 if (MASKED) mbytes[nfull] = (uint8_t)bits;
+            }
+            if (MASKED) {
+                brmin = __reduce_min_sync(0xffffffffu, brmin); brmax = __reduce_max_sync(0xffffffffu, brmax);
+                bcmin = __reduce_min_sync(0xffffffffu, bcmin); bcmax = __reduce_max_sync(0xffffffffu, bcmax);
+                if (lane == 0 && brmax >= 0) {
+                    atomicMin(&H.box[0], brmin); atomicMax(&H.box[1], brmax);
+                    atomicMin(&H.box[2], bcmin); atomicMax(&H.box[3], bcmax);
+                }
             }
             const uint32_t wm = __reduce_max_sync(0xffffffffu, max(mx2 & 0xffffu, mx2 >> 16));
             if (lane == 0) H.wmax[gw] = wm;
@@ -271,8 +300,11 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
         }
 
         // ---- 3. one GLCM per direction ----
+        // box of pixels that can take part in a pair: the tile, or the mask's bounding box
+        int bx[4] = {0, T.h - 1, 0, T.w - 1};
+        if (MASKED && active) { bx[0] = H.box[0]; bx[1] = H.box[1]; bx[2] = H.box[2]; bx[3] = H.box[3]; }
         for (int a = 0; a < P.n_angles; ++a) {
-            const K3Geom G = k3_geom(T.h, T.w, P.dr[a], P.dc[a]);
+            const K3Geom G = k3_geom(T.w, P.dr[a], P.dc[a], bx[0], bx[1], bx[2], bx[3]);
             uint32_t I4[kK3Cache], J4[kK3Cache], vm[kK3Cache];
             if (active) {
                 // table-free: pair-stream sums; the first kK3Cache items of a thread stay in registers
@@ -339,12 +371,15 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
         // ---- 4. epilogue: one lane per direction ----
         if (active) {
             ring_group_sync(R);                            // accumulators complete
+            // everyone read the mask box long ago; reset it before the next tile's stage 1 (one more
+            // group barrier follows below)
+            if (MASKED && gt == 32) { H.box[0] = 1 << 30; H.box[1] = -1; H.box[2] = 1 << 30; H.box[3] = -1; }
             if (gw == 0 && lane < P.n_angles) {
                 const int a = lane;
                 const uint32_t* s = H.acc[a];
                 const long long M = (long long)s[7];
                 // non-existent pairs that went through the branch-free path (unmasked only)
-                const K3Geom Ge = k3_geom(T.h, T.w, P.dr[a], P.dc[a]);
+                const K3Geom Ge = k3_geom(T.w, P.dr[a], P.dc[a], 0, T.h - 1, 0, T.w - 1);
                 const long long D = MASKED ? 0ll : 4ll * Ge.nrows * Ge.gpr - M;
                 const unsigned long long sold_true = (unsigned long long)s[6] - (unsigned long long)(D * (D - 1) / 2);
                 unsigned long long hom_sum = 0ull;
