@@ -30,6 +30,7 @@ struct K2Group {
 constexpr int kK2GfixSmem = 4096;  // entropy-table entries mirrored in shared memory
 struct K2Smem {
     uint32_t hist[32768];
+    uint32_t dummy[32];      // one word per lane, right behind the table: where pixels outside the mask go
     unsigned long long gfix[kK2GfixSmem];
     unsigned long long tokens[8];
     K2Group grp[8];
@@ -79,18 +80,38 @@ __device__ __forceinline__ void k2_vec(K2Smem& S, const Params& P, const uint4& 
 #pragma unroll
         for (int hlf = 0; hlf < 2; ++hlf) {
             const uint32_t x = hlf ? (w[k] >> 16) : (w[k] & 0xffffu);
-            if (MASKED && !(mb & (hlf ? 0xff00u : 0xffu))) continue;
-            if (PHASE == 0) {
-                const uint32_t old = k2_add(S, x);
-                if (olds) {
-                    olds[k] |= old << (16 * hlf);
+            if (!MASKED) {
+                if (PHASE == 0) {
+                    const uint32_t old = k2_add(S, x);
+                    if (olds) {
+                        olds[k] |= old << (16 * hlf);
+                    } else {
+                        acc += k2_gfix(S, P, old);
+                        maxold = max(maxold, old);
+                    }
                 } else {
-                    acc += k2_gfix(S, P, old);
-                    maxold = max(maxold, old);
+                    S.hist[x >> 1] = 0u;
                 }
-                if (MASKED) ++cnt;
             } else {
-                S.hist[x >> 1] = 0u;
+                // branch-free: a pixel outside the mask increments (and later clears) this lane's
+                // dummy word instead of a bin, and its returned count is replaced by 0 (G[0] = 0)
+                const bool in = (mb & (hlf ? 0xff00u : 0xffu)) != 0u;
+                const uint32_t off = in ? ((x << 1) & 0x1fffcu) : (0x20000u + 4u * (threadIdx.x & 31));
+                uint32_t* word = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(S.hist) + off);
+                if (PHASE == 0) {
+                    const uint32_t sh = in ? ((x & 1u) << 4) : 0u;
+                    uint32_t old = (atomicAdd(word, 1u << sh) >> sh) & 0xffffu;
+                    old = in ? old : 0u;
+                    cnt += in ? 1u : 0u;
+                    if (olds) {
+                        olds[k] |= old << (16 * hlf);
+                    } else {
+                        acc += k2_gfix(S, P, old);
+                        maxold = max(maxold, old);
+                    }
+                } else {
+                    *word = 0u;
+                }
             }
         }
     }
@@ -238,6 +259,7 @@ __global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_
 
     for (int k = tid; k < 32768; k += blockDim.x) S.hist[k] = 0u;
     if (gt < 32) G.coarse[gt] = 0u;
+    if (tid < 32) S.dummy[tid] = 0u;
     if (gt == 0) { G.constant = 0; G.cnt = 0u; }
     for (int k = tid; k < kK2GfixSmem; k += blockDim.x) S.gfix[k] = __ldg(P.gfix + k);
     __syncthreads();

@@ -34,7 +34,8 @@ struct K3GroupHdr {
 };
 struct K3Smem {
     uint32_t hist[32768];
-    uint32_t dummy[2];       // bin for the non-existent pairs of a partial group (unmasked path), at hist + 0x20000
+    uint32_t dummy[34];      // at hist + 0x20000: word 0 takes the non-existent pairs of the unmasked path,
+                             // words 2..33 (one per lane) those of the masked path
     double homtab[256];
     unsigned long long tokens[8];
 };
@@ -135,32 +136,29 @@ __device__ __forceinline__ void k3_sums(const K3Smem& S, uint32_t I4, uint32_t J
     A.sd += __vsadu4(I4, J4);
     A.m += __popc(vm) >> 3;
     const uint32_t D4 = __vabsdiffu4(I4, J4);
-    if (!MASKED) {
-        A.hom += S.homtab[D4 & 0xffu];
-        A.hom += S.homtab[(D4 >> 8) & 0xffu];
-        A.hom += S.homtab[(D4 >> 16) & 0xffu];
-        A.hom += S.homtab[D4 >> 24];
-    } else {
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-            if ((vm >> (8 * b)) & 1u) A.hom += S.homtab[(D4 >> (8 * b)) & 0xffu];
-    }
+    A.hom += S.homtab[D4 & 0xffu];
+    A.hom += S.homtab[(D4 >> 8) & 0xffu];
+    A.hom += S.homtab[(D4 >> 16) & 0xffu];
+    A.hom += S.homtab[D4 >> 24];
+    // masked tiles: take the 1.0 of every missing pair out again right away (exact)
+    if (MASKED) A.hom -= (double)(4 - (__popc(vm) >> 3));
 }
 
 // PHASE 0: bins += 1, accumulating the returned old counts (sum_bins c^2 = 2*sum(old) + M);
 // PHASE 2: sparse clear.  Keys (i << 8 | j) are assembled two at a time with PRMT.
-// Unmasked tiles run branch-free: a non-existent pair is redirected to the dummy bin behind the
-// table; D such pairs return the old values 0..D-1 in some order, so the epilogue subtracts
-// D(D-1)/2.  Masked tiles (many missing pairs) use predication instead.
+// Both variants run branch-free.  Unmasked: a non-existent pair (row tail) is redirected to one
+// dummy bin behind the table; D such pairs return the old values 0..D-1 in some order, so the
+// epilogue subtracts D(D-1)/2.  Masked (many missing pairs): each lane has its own dummy word and
+// the returned count of a missing pair is dropped with a select.
 template <int PHASE, bool MASKED>
 __device__ __forceinline__ void k3_bin1(K3Smem& S, uint32_t key, bool exists, uint32_t& sold) {
-    if (MASKED && !exists) return;
     uint32_t off = (key << 1) & 0x1fffcu;
-    if (!MASKED) off = exists ? off : 0x20000u;
+    off = exists ? off : (MASKED ? 0x20008u + 4u * (threadIdx.x & 31) : 0x20000u);
     uint32_t* word = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(S.hist) + off);
     if (PHASE == 0) {
         const uint32_t sh = (key & 1u) << 4;       // key == 0 for a non-existent pair
-        sold += (atomicAdd(word, 1u << sh) >> sh) & 0xffffu;
+        const uint32_t old = (atomicAdd(word, 1u << sh) >> sh) & 0xffffu;
+        sold += (MASKED && !exists) ? 0u : old;    // unmasked: corrected by D(D-1)/2 in the epilogue
     } else {
         *word = 0u;
     }
@@ -195,7 +193,7 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
 
     for (int k = tid; k < 32768; k += blockDim.x) S.hist[k] = 0u;
     if (tid < 256) S.homtab[tid] = 1.0 / (1.0 + (double)(tid * tid));
-    if (tid < 2) S.dummy[tid] = 0u;
+    if (tid < 34) S.dummy[tid] = 0u;
     if (gt == 0) { H.box[0] = 1 << 30; H.box[1] = -1; H.box[2] = 1 << 30; H.box[3] = -1; }
     if (gt < kMaxAngles * 8) H.acc[gt >> 3][gt & 7] = 0u;
     __syncthreads();
