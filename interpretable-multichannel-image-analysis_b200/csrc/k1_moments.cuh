@@ -58,8 +58,11 @@ __device__ __forceinline__ void k1_vec(const uint4& v, const uint2& m, unsigned 
             w[k] &= h[k];
             st.mx2 = __vmaxu2(st.mx2, w[k]);
             st.sum = __dp2a_lo(w[k], 0x0101u, st.sum);
-            if (h[k] & 0xffffu) k1_px(w[k] & 0xffffu, c64, st.S[0], st.S[1], st.S[2]);
-            if (h[k] >> 16) k1_px(w[k] >> 16, c64, st.S[3], st.S[4], st.S[5]);
+            // branch-free: a pixel outside the mask (already zeroed) gets the pivot-free bias, so
+            // its y is exactly 0 and adds nothing to the three sums
+            const unsigned long long cz = (c64 & 0xffffffff00000000ull) | (1ull << 20);
+            k1_px(w[k] & 0xffffu, (h[k] & 0xffffu) ? c64 : cz, st.S[0], st.S[1], st.S[2]);
+            k1_px(w[k] >> 16, (h[k] >> 16) ? c64 : cz, st.S[3], st.S[4], st.S[5]);
         }
     } else {
 #pragma unroll
