@@ -94,3 +94,39 @@ def test_synth_is_deterministic_and_in_range():
     assert 0.12 < min(fr) and max(fr) < 0.65
     h, w = synth.object_size(3, 5, 128, 128, True, 16, 16)
     assert 16 <= h <= 128 and 16 <= w <= 128
+
+
+def test_pinned_batcher_packing_cpu():
+    """Packing logic of the batcher (no GPU needed: a stub extractor records what it is given)."""
+    from imfeat_b200 import PinnedBatcher
+
+    class Stub:
+        calls = []
+
+        def row_width(self, c):
+            return 23 * c
+
+        def extract_host_hwc(self, images, masks=None, sizes=None):
+            self.calls.append((images.copy(), None if masks is None else masks.copy(),
+                               None if sizes is None else sizes.copy()))
+            return np.full((images.shape[0], 23 * images.shape[3]), float(len(self.calls)))
+
+    rng = np.random.default_rng(0)
+    stub = Stub()
+    b = PinnedBatcher(stub, capacity=3, hs=16, ws=12, channels=2, with_masks=True)
+    objs = [(rng.integers(0, 4096, (h, w, 2)).astype(np.uint16), rng.random((h, w, 2)) < 0.5)
+            for h, w in [(16, 12), (9, 7), (16, 12), (5, 12), (16, 12)]]
+    for k, (img, m) in enumerate(objs):
+        b.add(img, m, label="o%d" % k)
+    table, labels = b.finish()
+    assert table.shape == (5, 46) and labels == ["o%d" % k for k in range(5)]
+    assert len(stub.calls) == 2                            # a full slab of 3, then the tail of 2
+    imgs, masks, sizes = stub.calls[0]
+    assert sizes.tolist() == [[16, 12], [9, 7], [16, 12]]
+    assert (imgs[1, :9, :7] == objs[1][0]).all() and (masks[1, :9, :7] == objs[1][1]).all()
+    imgs, masks, sizes = stub.calls[1]
+    assert sizes.tolist() == [[5, 12], [16, 12]]
+    with pytest.raises(ValueError):
+        b.add(np.zeros((17, 12, 2), np.uint16), np.zeros((17, 12, 2), bool))
+    with pytest.raises(ValueError):
+        b.add(np.zeros((4, 4, 2), np.float32), np.zeros((4, 4, 2), bool))
