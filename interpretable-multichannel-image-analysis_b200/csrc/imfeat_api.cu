@@ -25,7 +25,9 @@ constexpr int kTimingSlots = 64;
 struct imfeat_ctx {
     int device;
     int sm_count;
-    int k1_bps[2], k4_bps[2];   // resident CTAs per SM (occupancy API), [masked]
+    int k1_bps[2], k4_bps[2], k2c_bps[2];   // resident CTAs per SM (occupancy API), [masked]
+    uint32_t* d_worklist;       // [0] = count, [1..] = tile ids left to the full-range K2 kernel
+    size_t worklist_cap;
     double* d_log2tab;
     unsigned long long* d_gfix;
     long long launches;
@@ -145,6 +147,8 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_moments_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_bps[0], k1_moments_kernel<false>, 256, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_bps[1], k1_moments_kernel<true>, 256, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2c_bps[0], k2c_order_entropy_kernel<false>, kK2cThreads, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2c_bps[1], k2c_order_entropy_kernel<true>, kK2cThreads, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4_bps[0], k4_shape_kernel<false>, kK4Threads, sizeof(K4Smem));
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4_bps[1], k4_shape_kernel<true>, kK4Threads, sizeof(K4Smem));
     if (e != cudaSuccess) {
@@ -182,6 +186,7 @@ int imfeat_destroy(imfeat_ctx* ctx) {
             if (ctx->t_ev[sl][k]) cudaEventDestroy(ctx->t_ev[sl][k]);
     if (ctx->d_log2tab) cudaFree(ctx->d_log2tab);
     if (ctx->d_gfix) cudaFree(ctx->d_gfix);
+    if (ctx->d_worklist) cudaFree(ctx->d_worklist);
     free(ctx);
     return IMFEAT_OK;
 }
@@ -321,10 +326,32 @@ static int launch_all(imfeat_ctx* ctx, const Params& P, const imfeat_opts* o, cu
         IMFEAT_MARK(0)
         const int g2 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
         const int ng2 = k2_groups(masked);
-        if (masked) k2_order_entropy_kernel<true><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2);
-        else k2_order_entropy_kernel<false><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2);
+        const char* k2cenv = getenv("IMFEAT_K2_COMPACT");
+        if (k2cenv && atoi(k2cenv) == 0) {
+            // full-range kernel for every tile
+            if (masked) k2_order_entropy_kernel<true><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, nullptr, nullptr);
+            else k2_order_entropy_kernel<false><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, nullptr, nullptr);
+            ctx->launches += 2;
+        } else {
+            // compact kernel first (value range < 4096, known from K1's min/max); it appends the
+            // remaining tiles to a worklist that the full-range ring kernel then works off
+            if ((size_t)P.n_tiles + 1 > ctx->worklist_cap) {
+                if (ctx->d_worklist) CU(cudaFree(ctx->d_worklist));
+                ctx->d_worklist = nullptr;
+                ctx->worklist_cap = 0;
+                CU(cudaMalloc((void**)&ctx->d_worklist, sizeof(uint32_t) * ((size_t)P.n_tiles + 1)));
+                ctx->worklist_cap = (size_t)P.n_tiles + 1;
+            }
+            CU(cudaMemsetAsync(ctx->d_worklist, 0, sizeof(uint32_t), st));
+            const long long resc = sm * (ctx->k2c_bps[masked] > 0 ? ctx->k2c_bps[masked] : 1);
+            const int gc = (int)(P.n_tiles < resc ? P.n_tiles : resc);
+            if (masked) k2c_order_entropy_kernel<true><<<gc, kK2cThreads, 0, st>>>(P, ctx->d_worklist + 1, ctx->d_worklist);
+            else k2c_order_entropy_kernel<false><<<gc, kK2cThreads, 0, st>>>(P, ctx->d_worklist + 1, ctx->d_worklist);
+            if (masked) k2_order_entropy_kernel<true><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, ctx->d_worklist + 1, ctx->d_worklist);
+            else k2_order_entropy_kernel<false><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, ctx->d_worklist + 1, ctx->d_worklist);
+            ctx->launches += 3;
+        }
         IMFEAT_MARK(1)
-        ctx->launches += 2;
     }
     if (o->want_glcm) {
         const int g3 = (int)(P.n_tiles < sm ? P.n_tiles : sm);

@@ -248,7 +248,9 @@ __device__ __forceinline__ void k2_percentiles(K2Smem& S, const uint32_t* coarse
 }
 
 template <bool MASKED>
-__global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_constant__ Params P, int ng) {
+__global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_constant__ Params P, int ng,
+                                                                   const uint32_t* __restrict__ worklist,
+                                                                   const uint32_t* __restrict__ worklist_count) {
     extern __shared__ __align__(16) unsigned char k2_smem_raw[];
     K2Smem& S = *reinterpret_cast<K2Smem*>(k2_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -264,12 +266,19 @@ __global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_
     for (int k = tid; k < kK2GfixSmem; k += blockDim.x) S.gfix[k] = __ldg(P.gfix + k);
     __syncthreads();
 
+    // With a worklist (tiles the compact kernel k2c could not take: value range >= 4096) only those
+    // tiles are processed; otherwise all tiles.
+    const long long total = worklist ? (long long)*worklist_count : P.n_tiles;
     const long long first = blockIdx.x;
-    const long long mine = first < P.n_tiles ? (P.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
+    const long long mine = first < total ? (total - first + gridDim.x - 1) / gridDim.x : 0;
     const long long n_iter = (mine + ng - 1) / ng;
     TileWalk walk;
-    walk.init(P, first + (long long)g * gridDim.x < P.n_tiles ? first + (long long)g * gridDim.x : 0,
+    walk.init(P, first + (long long)g * gridDim.x < total ? first + (long long)g * gridDim.x : 0,
               (long long)ng * gridDim.x);
+    auto resolve_k = [&](long long k) -> Tile {      // k-th tile of this CTA (k = ng*it + g)
+        if (worklist) return resolve_tile(P, (long long)worklist[first + k * gridDim.x]);
+        return resolve_tile_rs(P, walk.row, walk.slot);
+    };
 
     // The pixels of a tile live in registers; the next tile's loads are issued right after the
     // table has been handed over, so HBM latency hides behind the current tile's epilogue and the
@@ -292,7 +301,7 @@ __global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_
             }
         }
     };
-    if (active) { T = resolve_tile_rs(P, walk.row, walk.slot); fetch(T); }
+    if (active) { T = resolve_k(g); fetch(T); }
 
     for (long long it = 0; it < n_iter; ++it) {
         uint32_t cnt = 0, maxold = 0;
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_
         const bool was_active = active;
         walk.next();
         active = (long long)ng * (it + 1) + g < mine;
-        if (active) { T = resolve_tile_rs(P, walk.row, walk.slot); fetch(T); }
+        if (active) { T = resolve_k((long long)ng * (it + 1) + g); fetch(T); }
 
         if (was_active) {
             // entropy terms of the register-resident pixels: G[old], looked up off the critical path
@@ -362,6 +371,174 @@ __global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_
                 G.constant = 0;
             }
         }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K2c: compact variant for tiles whose value range (max - min, both already in the table from K1)
+// is below 4,096 -- all 12-bit data.  The histogram is then 4,096 bins relative to the minimum
+// (8 KB), private to a 256-thread CTA, so several CTAs run per SM with no table hand-over at all;
+// the percentile walk starts at bin 0 (= the minimum) and the clear is a dense store over the used
+// range.  Tiles with a wider range are appended to a worklist for the full-range ring kernel above.
+// -------------------------------------------------------------------------------------------------
+constexpr int kK2cThreads = 256;
+constexpr int kK2cWarps = kK2cThreads / 32;
+constexpr int kK2cBins = 4096;
+constexpr int kK2cWords = kK2cBins / 2;
+
+struct K2cSmem {
+    uint32_t hist[kK2cWords];
+    uint32_t dummy[32];
+    int vals[18];
+    uint32_t cnt;
+    int constant;
+    unsigned long long wacc[kK2cWarps];
+};
+
+template <bool MASKED>
+__device__ __forceinline__ void k2c_px(K2cSmem& S, const Params& P, uint32_t x, bool in, uint32_t vmin,
+                                       uint32_t& cnt, uint32_t& maxold, unsigned long long& acc) {
+    const uint32_t bin = x - vmin;
+    uint32_t off = (bin << 1) & (uint32_t)(kK2cWords * 4 - 4);
+    uint32_t sh = (bin & 1u) << 4;
+    if (MASKED) {                                        // branch-free: outside the mask -> this lane's dummy word
+        off = in ? off : (uint32_t)(kK2cWords * 4) + 4u * (threadIdx.x & 31);
+        sh = in ? sh : 0u;
+    }
+    uint32_t* word = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(S.hist) + off);
+    uint32_t old = (atomicAdd(word, 1u << sh) >> sh) & 0xffffu;
+    if (MASKED) { old = in ? old : 0u; cnt += in ? 1u : 0u; }
+    acc += __ldg(P.gfix + old);
+    maxold = max(maxold, old);
+}
+
+template <bool MASKED>
+__global__ void __launch_bounds__(kK2cThreads, 4) k2c_order_entropy_kernel(const __grid_constant__ Params P,
+                                                                          uint32_t* __restrict__ worklist,
+                                                                          uint32_t* __restrict__ worklist_count) {
+    __shared__ K2cSmem S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < kK2cWords; k += kK2cThreads) S.hist[k] = 0u;
+    if (tid < 32) S.dummy[tid] = 0u;
+    if (tid == 0) { S.cnt = 0u; S.constant = 0; }
+    __syncthreads();
+
+    TileWalk walk;
+    walk.init(P, blockIdx.x < P.n_tiles ? blockIdx.x : 0, gridDim.x);
+    for (long long t = blockIdx.x; t < P.n_tiles; t += gridDim.x, walk.next()) {
+        const Tile T = resolve_tile_rs(P, walk.row, walk.slot);
+        double* o = T.out_row + P.col_basic + kNBasic * T.slot;
+        const double dmin = o[0], dmax = o[10];              // written by K1 (earlier launch, same stream)
+        if (!(dmin == dmin)) {                               // NaN: no pixel inside the mask
+            if (tid == 0) {
+                const double nan = qnan();
+#pragma unroll
+                for (int q = 1; q <= 9; ++q) o[q] = nan;
+                o[16] = nan;
+            }
+            continue;
+        }
+        const uint32_t vmin = (uint32_t)dmin, range = (uint32_t)dmax - vmin;
+        if (range >= (uint32_t)kK2cBins) {                   // too wide: leave it to the full-range kernel
+            if (tid == 0) worklist[atomicAdd(worklist_count, 1u)] = (uint32_t)t;
+            continue;
+        }
+        const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
+        const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
+        const int nfull = T.n >> 3, rem = T.n & 7;
+        uint32_t cnt = 0, maxold = 0;
+        unsigned long long acc = 0ull;
+        for (int idx = tid; idx < nfull; idx += kK2cThreads) {
+            const uint4 v = ld_stream(px4 + idx);
+            uint2 m = make_uint2(0u, 0u);
+            if (MASKED) m = __ldg(mk2 + idx);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t mb = (k < 2 ? m.x : m.y) >> (16 * (k & 1));
+                k2c_px<MASKED>(S, P, w[k] & 0xffffu, (mb & 0xffu) != 0u, vmin, cnt, maxold, acc);
+                k2c_px<MASKED>(S, P, w[k] >> 16, (mb & 0xff00u) != 0u, vmin, cnt, maxold, acc);
+            }
+        }
+        if (tid < rem) {
+            const int i = nfull * 8 + tid;
+            const bool in = !MASKED || T.mk[i] != 0;
+            if (in) {
+                uint32_t c1 = 0;
+                k2c_px<false>(S, P, T.px[i], true, vmin, c1, maxold, acc);
+                cnt += 1;
+            }
+        }
+        if (MASKED) {
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0 && cnt) atomicAdd(&S.cnt, cnt);
+        }
+        __syncthreads();                                     // histogram complete
+        const int n = MASKED ? (int)S.cnt : T.n;
+        if (warp == 0 && n > 0) {
+            // numpy percentile (method "linear"); dense walk from bin 0 = the minimum
+            int lo[9], hi[9], maxrank = 0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const double virt = __dmul_rn((double)(n - 1), P.quant[k]);
+                if (virt >= (double)(n - 1)) { lo[k] = hi[k] = n - 1; }
+                else { lo[k] = (int)floor(virt); hi[k] = lo[k] + 1; }
+                maxrank = max(maxrank, hi[k]);
+            }
+            int cum = 0;
+            for (int block = 0; block * 64 <= (int)range; ++block) {
+                const uint32_t wv = S.hist[block * 32 + lane];
+                const int c0 = wv & 0xffffu, c1 = wv >> 16, tot = c0 + c1;
+                int incl = tot;
+#pragma unroll
+                for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o2);
+                    if (lane >= o2) incl += v;
+                }
+                const int r0 = cum + incl - tot, r1 = cum + incl;
+                const int base = (int)vmin + block * 64 + 2 * lane;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    if (lo[k] >= r0 && lo[k] < r1) S.vals[2 * k] = base + (lo[k] >= r0 + c0);
+                    if (hi[k] >= r0 && hi[k] < r1) S.vals[2 * k + 1] = base + (hi[k] >= r0 + c0);
+                }
+                cum += __shfl_sync(0xffffffffu, incl, 31);
+                if (cum > maxrank) break;
+            }
+            __syncwarp();
+            if (lane < 9) {
+                const double virt = __dmul_rn((double)(n - 1), P.quant[lane]);
+                const double g = virt - floor(virt);
+                const int a = S.vals[2 * lane], b = S.vals[2 * lane + 1];
+                const double diff = (double)(b - a);
+                o[1 + lane] = (g >= 0.5) ? __dsub_rn((double)b, __dmul_rn(diff, __dsub_rn(1.0, g)))
+                                         : __dadd_rn((double)a, __dmul_rn(diff, g));
+            }
+        }
+        if (n > 0 && (int)maxold + 1 == n) S.constant = 1;   // one value only: entropy is exactly 0
+        acc = warp_sum_redux(acc);
+        if (lane == 0) S.wacc[warp] = acc;
+        __syncthreads();                                     // walk done; n read; partial sums visible
+        const int used_words = (int)(range >> 1) + 1;
+        for (int k = tid; k < used_words; k += kK2cThreads) S.hist[k] = 0u;
+        if (MASKED && tid < 32) S.dummy[tid] = 0u;
+        if (tid == 0) {
+            if (n > 0) {
+                unsigned long long tot = 0ull;
+#pragma unroll
+                for (int w = 0; w < kK2cWarps; ++w) tot += S.wacc[w];
+                const double H = __ldg(P.log2tab + n) - ((double)tot * 2.2737367544323206e-13) / (double)n;
+                o[16] = S.constant ? 0.0 : H;
+            } else {
+                const double nan = qnan();
+#pragma unroll
+                for (int q = 1; q <= 9; ++q) o[q] = nan;
+                o[16] = nan;
+            }
+            S.constant = 0;
+            S.cnt = 0u;
+        }
+        __syncthreads();                                     // table clean, scratch consumed
     }
 }
 
