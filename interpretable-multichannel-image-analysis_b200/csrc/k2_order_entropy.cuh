@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_
 // the percentile walk starts at bin 0 (= the minimum) and the clear is a dense store over the used
 // range.  Tiles with a wider range are appended to a worklist for the full-range ring kernel above.
 // -------------------------------------------------------------------------------------------------
-constexpr int kK2cThreads = 256;
+constexpr int kK2cThreads = 32;
 constexpr int kK2cWarps = kK2cThreads / 32;
 constexpr int kK2cBins = 4096;
 constexpr int kK2cWords = kK2cBins / 2;
@@ -413,7 +413,7 @@ __device__ __forceinline__ void k2c_px(K2cSmem& S, const Params& P, uint32_t x, 
 }
 
 template <bool MASKED>
-__global__ void __launch_bounds__(kK2cThreads, 4) k2c_order_entropy_kernel(const __grid_constant__ Params P,
+__global__ void __launch_bounds__(kK2cThreads, 24) k2c_order_entropy_kernel(const __grid_constant__ Params P,
                                                                           uint32_t* __restrict__ worklist,
                                                                           uint32_t* __restrict__ worklist_count) {
     __shared__ K2cSmem S;
