@@ -25,7 +25,7 @@ constexpr int kTimingSlots = 64;
 struct imfeat_ctx {
     int device;
     int sm_count;
-    int k1_bps[2], k4_bps[2], k2c_bps[2];   // resident CTAs per SM (occupancy API), [masked]
+    int k1_bps[2], k4_bps[2], k2c_bps[2], k4w_bps[2];   // resident CTAs per SM (occupancy API), [masked]
     uint32_t* d_worklist;       // [0] = count, [1..] = tile ids left to the full-range K2 kernel
     size_t worklist_cap;
     double* d_log2tab;
@@ -149,6 +149,8 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_bps[1], k1_moments_kernel<true>, 256, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2c_bps[0], k2c_order_entropy_kernel<false>, kK2cThreads, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2c_bps[1], k2c_order_entropy_kernel<true>, kK2cThreads, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4w_bps[0], k4w_shape_kernel<false>, 32, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4w_bps[1], k4w_shape_kernel<true>, 32, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4_bps[0], k4_shape_kernel<false>, kK4Threads, sizeof(K4Smem));
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4_bps[1], k4_shape_kernel<true>, kK4Threads, sizeof(K4Smem));
     if (e != cudaSuccess) {
@@ -363,10 +365,21 @@ static int launch_all(imfeat_ctx* ctx, const Params& P, const imfeat_opts* o, cu
         ctx->launches += 1;
     }
     if (o->want_shape || o->want_moments) {
-        const long long res4 = sm * (ctx->k4_bps[masked] > 0 ? ctx->k4_bps[masked] : 1);
-        const int g4 = (int)(P.n_tiles < res4 ? P.n_tiles : res4);
-        if (masked) k4_shape_kernel<true><<<g4, kK4Threads, sizeof(K4Smem), st>>>(P);
-        else k4_shape_kernel<false><<<g4, kK4Threads, sizeof(K4Smem), st>>>(P);
+        const char* k4env = getenv("IMFEAT_K4_WARP");
+        const bool warp_tiles = P.hs <= kK4FastDim && P.ws <= kK4FastDim && P.hs * P.ws <= kK4FastPixels &&
+                                !(k4env && atoi(k4env) == 0);
+        if (warp_tiles) {
+            // every tile of this batch fits the fast path: one warp per tile, many warps per SM
+            const long long resw = sm * (ctx->k4w_bps[masked] > 0 ? ctx->k4w_bps[masked] : 1);
+            const int gw = (int)(P.n_tiles < resw ? P.n_tiles : resw);
+            if (masked) k4w_shape_kernel<true><<<gw, 32, 0, st>>>(P);
+            else k4w_shape_kernel<false><<<gw, 32, 0, st>>>(P);
+        } else {
+            const long long res4 = sm * (ctx->k4_bps[masked] > 0 ? ctx->k4_bps[masked] : 1);
+            const int g4 = (int)(P.n_tiles < res4 ? P.n_tiles : res4);
+            if (masked) k4_shape_kernel<true><<<g4, kK4Threads, sizeof(K4Smem), st>>>(P);
+            else k4_shape_kernel<false><<<g4, kK4Threads, sizeof(K4Smem), st>>>(P);
+        }
         IMFEAT_MARK(3)
         ctx->launches += 1;
     }

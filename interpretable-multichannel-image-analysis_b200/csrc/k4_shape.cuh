@@ -361,3 +361,136 @@ __global__ void __launch_bounds__(kK4Threads, 3) k4_shape_kernel(const __grid_co
 }
 
 }  // namespace imfeat
+
+// -------------------------------------------------------------------------------------------------
+// K4w: one WARP per tile (32-thread CTAs, many per SM) for batches whose stride fits the fast path
+// (Hs, Ws <= 256, Hs*Ws <= 16384).  Same arithmetic as the fast path above, but with no CTA-wide
+// barrier, no cross-warp reduction and no staging pass: rows are read straight from global memory
+// (four rows in flight per lane) and latency is hidden by occupancy.
+// -------------------------------------------------------------------------------------------------
+namespace imfeat {
+
+constexpr int kK4wWords = 1024;     // >= h * ceil(w/32) under the fast-path limits (<= 768)
+
+template <bool MASKED>
+__global__ void __launch_bounds__(32, 20) k4w_shape_kernel(const __grid_constant__ Params P) {
+    __shared__ uint32_t mrow[kK4wWords];
+    __shared__ uint32_t brow[kK4wWords];
+    const int lane = threadIdx.x;
+    const bool want_mom = P.col_moment >= 0;
+
+    TileWalk walk;
+    walk.init(P, blockIdx.x < P.n_tiles ? blockIdx.x : 0, gridDim.x);
+    for (long long t = blockIdx.x; t < P.n_tiles; t += gridDim.x, walk.next()) {
+        const Tile T = resolve_tile_rs(P, walk.row, walk.slot);
+        const int h = T.h, w = T.w;
+        const int Pw = (w + 31) >> 5;
+        int rmin = 1 << 30, rmax = -1, cmin = 1 << 30, cmax = -1;
+        uint32_t area = 0, sr = 0, sc = 0, srr = 0, scc = 0, src = 0;
+        unsigned long long mq[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // M00 M10 M01 M20 M11 M02 M30 M21 M12 M03
+
+        // ---- pass A: lanes over columns, rows in sequence (four rows of loads in flight) ----
+        for (int c0 = 0; c0 < w; c0 += 32) {
+            const int c = c0 + lane;
+            const bool inb = c < w;
+            uint32_t cnt = 0, csr = 0, csrr = 0, b0 = 0, b1 = 0;
+            unsigned long long b2 = 0, b3 = 0;
+            const uint8_t* mp = T.mk + (inb ? c : 0);
+            const uint16_t* pp = T.px + (inb ? c : 0);
+            uint32_t* mr = mrow + (c0 >> 5);
+            auto row = [&](int r, bool m, uint32_t pxv) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, m);
+                if (lane == 0) mr[r * Pw] = bal;
+                const uint32_t m1 = m ? 1u : 0u, im = m ? pxv : 0u;
+                const uint32_t r1 = r, r2 = r * r, r3 = r2 * r;
+                cnt += m1; csr += m1 * r1; csrr += m1 * r2;
+                rmin = m ? min(rmin, r) : rmin; rmax = m ? max(rmax, r) : rmax;
+                b0 += im; b1 += im * r1;
+                b2 += (unsigned long long)im * r2;
+                b3 += (unsigned long long)im * r3;
+            };
+            int r = 0;
+            for (; r + 4 <= h; r += 4) {
+                bool m[4];
+                uint32_t pxv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    m[u] = inb && (!MASKED || mp[(r + u) * w] != 0);
+                    pxv[u] = (want_mom && inb) ? (uint32_t)pp[(r + u) * w] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) row(r + u, m[u], pxv[u]);
+            }
+            for (; r < h; ++r) {
+                const bool m = inb && (!MASKED || mp[r * w] != 0);
+                row(r, m, (want_mom && inb) ? (uint32_t)pp[r * w] : 0u);
+            }
+            if (cnt) { cmin = min(cmin, c); cmax = max(cmax, c); }
+            const uint32_t c1 = inb ? c : 0, c2 = c1 * c1, c3 = c2 * c1;
+            area += cnt; sr += csr; srr += csrr; sc += c1 * cnt; scc += c2 * cnt; src += c1 * csr;
+            if (want_mom) {
+                mq[0] += b0; mq[1] += b1; mq[3] += b2; mq[6] += b3;
+                mq[2] += (unsigned long long)b0 * c1; mq[4] += (unsigned long long)b1 * c1;
+                mq[7] += b2 * c1;
+                mq[5] += (unsigned long long)b0 * c2; mq[8] += (unsigned long long)b1 * c2;
+                mq[9] += (unsigned long long)b0 * c3;
+            }
+        }
+        __syncwarp();
+        // ---- pass B: border = mask & ~erosion4(mask), 32 pixels per word ----
+        const int words = h * Pw;
+        for (int idx = lane; idx < words; idx += 32) {
+            const int r = idx / Pw, cw = idx - r * Pw;
+            const uint32_t m = mrow[idx];
+            const uint32_t up = r > 0 ? mrow[idx - Pw] : 0u, dn = r + 1 < h ? mrow[idx + Pw] : 0u;
+            const uint32_t ml = cw > 0 ? mrow[idx - 1] : 0u, mr2 = cw + 1 < Pw ? mrow[idx + 1] : 0u;
+            const uint32_t L = (m << 1) | (ml >> 31), Rr = (m >> 1) | (mr2 << 31);
+            brow[idx] = m & ~(up & dn & L & Rr);
+        }
+        __syncwarp();
+        // ---- pass C: classify border pixels by their 3x3 border neighbourhood ----
+        uint32_t n1 = 0, n2 = 0, n3 = 0;
+        for (int idx = lane; idx < words; idx += 32) {
+            const uint32_t b = brow[idx];
+            if (!b) continue;
+            const int r = idx / Pw, cw = idx - r * Pw;
+            const bool hu = r > 0, hd = r + 1 < h, hl = cw > 0, hr = cw + 1 < Pw;
+            const uint32_t bl = hl ? brow[idx - 1] : 0u, br = hr ? brow[idx + 1] : 0u;
+            const uint32_t u = hu ? brow[idx - Pw] : 0u, ul = (hu && hl) ? brow[idx - Pw - 1] : 0u;
+            const uint32_t ur = (hu && hr) ? brow[idx - Pw + 1] : 0u;
+            const uint32_t d = hd ? brow[idx + Pw] : 0u, dl = (hd && hl) ? brow[idx + Pw - 1] : 0u;
+            const uint32_t dr = (hd && hr) ? brow[idx + Pw + 1] : 0u;
+            const uint32_t N = u, Sd = d, W = (b << 1) | (bl >> 31), E = (b >> 1) | (br << 31);
+            const uint32_t NW = (u << 1) | (ul >> 31), NE = (u >> 1) | (ur << 31);
+            const uint32_t SW = (d << 1) | (dl >> 31), SE = (d >> 1) | (dr << 31);
+            uint32_t s1 = N ^ Sd ^ W, c1 = (N & Sd) | (N & W) | (Sd & W);
+            const uint32_t o0 = s1 ^ E, c2 = s1 & E, o1 = c1 ^ c2, o2 = c1 & c2;
+            s1 = NW ^ NE ^ SW; c1 = (NW & NE) | (NW & SW) | (NE & SW);
+            const uint32_t d0 = s1 ^ SE, c3 = s1 & SE, d1 = c1 ^ c3, d2 = c1 & c3;
+            const uint32_t o_is0 = ~o0 & ~o1 & ~o2, o_is1 = o0 & ~o1 & ~o2, o_23 = o1 & ~o2;
+            const uint32_t d_is1 = d0 & ~d1 & ~d2, d_is2 = ~d0 & d1 & ~d2, d_is3 = d0 & d1 & ~d2;
+            const uint32_t d_le2 = ~d2 & ~(d1 & d0);
+            n1 += __popc(b & o_23 & d_le2);
+            n2 += __popc(b & ((o_is0 & d_is2) | (o_is1 & d_is3)));
+            n3 += __popc(b & o_is1 & (d_is1 | d_is2));
+        }
+        // ---- warp totals (every lane gets them) and the two epilogues on two lanes ----
+        unsigned long long s[9];
+        s[0] = __reduce_add_sync(0xffffffffu, area); s[1] = __reduce_add_sync(0xffffffffu, sr);
+        s[2] = __reduce_add_sync(0xffffffffu, sc);   s[3] = __reduce_add_sync(0xffffffffu, srr);
+        s[4] = __reduce_add_sync(0xffffffffu, scc);  s[5] = __reduce_add_sync(0xffffffffu, src);
+        s[6] = __reduce_add_sync(0xffffffffu, n1);   s[7] = __reduce_add_sync(0xffffffffu, n2);
+        s[8] = __reduce_add_sync(0xffffffffu, n3);
+        rmin = __reduce_min_sync(0xffffffffu, rmin); rmax = __reduce_max_sync(0xffffffffu, rmax);
+        cmin = __reduce_min_sync(0xffffffffu, cmin); cmax = __reduce_max_sync(0xffffffffu, cmax);
+        if (want_mom) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) mq[k] = warp_sum_redux(mq[k]);
+        }
+        if (lane == 0 && P.col_shape >= 0) k4_shape_epilogue(P, T, s, rmin, rmax, cmin, cmax);
+        if (lane == 1 && want_mom) k4_moment_epilogue(P, T, mq);
+        __syncwarp();                                        // mrow / brow are rewritten by the next tile
+    }
+}
+
+}  // namespace imfeat
