@@ -27,10 +27,12 @@ constexpr int kK3Cache = 4;     // pair groups (4 pairs each) per thread cached 
 
 // Shared-memory layout (dynamic): [hist 128 KB][homtab 2 KB][tokens][per-group: K3GroupHdr, q8, mbits]
 struct K3GroupHdr {
-    unsigned long long whom[kMaxAngles][16];   // per-warp sums of 1/(1+d^2) in 2^-40 fixed point
-    uint32_t acc[kMaxAngles][8];               // si sj sii sjj sij sd sold m, per direction
+    // per-tile scratch exists twice and alternates: a tile's epilogue runs while the next tile is
+    // already under way (after that tile's staging barrier), so no barrier is spent on it
+    unsigned long long whom[2][kMaxAngles][16];   // per-warp sums of 1/(1+d^2) in 2^-40 fixed point
+    uint32_t acc[2][kMaxAngles][8];               // si sj sii sjj sij sd sold m, per direction
+    int box[2][4];                                // mask bounding box: rmin, rmax, cmin, cmax (masked variant)
     uint32_t wmax[32];
-    int box[4];                                // mask bounding box: rmin, rmax, cmin, cmax (masked variant)
 };
 struct K3Smem {
     uint32_t hist[32768];
@@ -173,6 +175,36 @@ __device__ __forceinline__ void k3_bins(K3Smem& S, uint32_t I4, uint32_t J4, uin
     k3_bin1<PHASE, MASKED>(S, K23 >> 16, (vm & 0x01000000u) != 0u, sold);
 }
 
+// One direction's six properties from the exact integer sums (s: si sj sii sjj sij sd sold m).
+template <bool MASKED>
+__device__ __forceinline__ void k3_epilogue(const Params& P, double* out_row, uint32_t* status, int slot,
+                                            int h, int w, int a, const uint32_t* s, unsigned long long hom_sum) {
+    const long long M = (long long)s[7];
+    double* o = out_row + P.col_glcm + (slot * P.n_angles + a) * kNGlcm;
+    if (M == 0) {
+        o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 0.0; o[4] = 0.0; o[5] = 1.0;
+        if (status) atomicOr(status, kStNoPairs);
+        return;
+    }
+    // non-existent pairs that went through the branch-free path (unmasked only)
+    const K3Geom Ge = k3_geom(w, P.dr[a], P.dc[a], 0, h - 1, 0, w - 1);
+    const long long D = MASKED ? 0ll : 4ll * Ge.nrows * Ge.gpr - M;
+    const unsigned long long sold_true = (unsigned long long)s[6] - (unsigned long long)(D * (D - 1) / 2);
+    const unsigned long long hom_true = hom_sum - ((unsigned long long)D << 40);
+    const double Md = (double)M;
+    const long long con = (long long)s[2] + (long long)s[3] - 2ll * (long long)s[4];
+    const long long vi = M * (long long)s[2] - (long long)s[0] * (long long)s[0];
+    const long long vj = M * (long long)s[3] - (long long)s[1] * (long long)s[1];
+    const long long cov = M * (long long)s[4] - (long long)s[0] * (long long)s[1];
+    const double asmv = (double)(2ull * sold_true + (unsigned long long)M) / (Md * Md);
+    o[0] = (double)con / Md;
+    o[1] = (double)s[5] / Md;
+    o[2] = ((double)hom_true * 9.094947017729282e-13) / Md;
+    o[3] = asmv;
+    o[4] = sqrt(asmv);
+    o[5] = (vi == 0 || vj == 0) ? 1.0 : (double)cov / (sqrt((double)vi) * sqrt((double)vj));
+}
+
 template <bool MASKED, bool DUMP>
 __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant__ Params P, int ng, int max_pixels) {
     extern __shared__ __align__(16) unsigned char k3_smem_raw[];
@@ -194,9 +226,30 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
     for (int k = tid; k < 32768; k += blockDim.x) S.hist[k] = 0u;
     if (tid < 256) S.homtab[tid] = 1.0 / (1.0 + (double)(tid * tid));
     if (tid < 34) S.dummy[tid] = 0u;
-    if (gt == 0) { H.box[0] = 1 << 30; H.box[1] = -1; H.box[2] = 1 << 30; H.box[3] = -1; }
-    if (gt < kMaxAngles * 8) H.acc[gt >> 3][gt & 7] = 0u;
+    if (gt < 2) { H.box[gt][0] = 1 << 30; H.box[gt][1] = -1; H.box[gt][2] = 1 << 30; H.box[gt][3] = -1; }
+    if (gt < 2 * kMaxAngles * 8) (&H.acc[0][0][0])[gt] = 0u;
     __syncthreads();
+    // K1 (same stream, earlier launch) already wrote the tile maximum into the table when the basic
+    // block is requested; then the max pass and its barrier are skipped.
+    const bool k1_max = P.col_basic >= 0;
+    // deferred epilogue of this group's previous tile
+    bool prev_active = false;
+    double* prev_row = nullptr;
+    uint32_t* prev_status = nullptr;
+    int prev_slot = 0, prev_h = 0, prev_w = 0;
+    auto deferred_epilogue = [&](int pbuf) {
+        if (prev_active && gw < P.n_angles && lane == 0) {
+            unsigned long long hom_sum = 0ull;
+            for (int w = 0; w < R.gwarps; ++w) hom_sum += H.whom[pbuf][gw][w];
+            k3_epilogue<MASKED>(P, prev_row, prev_status, prev_slot, prev_h, prev_w, gw, H.acc[pbuf][gw], hom_sum);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) H.acc[pbuf][gw][k] = 0u;
+        }
+        if (MASKED && prev_active && gt == 0) {
+            H.box[pbuf][0] = 1 << 30; H.box[pbuf][1] = -1; H.box[pbuf][2] = 1 << 30; H.box[pbuf][3] = -1;
+        }
+        prev_active = false;
+    };
 
     const long long first = blockIdx.x;
     const long long mine = first < P.n_tiles ? (P.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
@@ -205,6 +258,7 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
     walk.init(P, first + (long long)g * gridDim.x < P.n_tiles ? first + (long long)g * gridDim.x : 0,
               (long long)ng * gridDim.x);
     for (long long it = 0; it < n_iter; ++it, walk.next()) {
+        const int buf = (int)(it & 1);
         const long long kk = (long long)ng * it + g;
         const bool active = kk < mine;
         const long long t = first + kk * gridDim.x;
@@ -220,8 +274,11 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
             // ---- 1. tile maximum (over the mask when masked); stage the mask bits and their bounding box ----
             uint32_t mx2 = 0u;
             int brmin = 1 << 30, brmax = -1, bcmin = 1 << 30, bcmax = -1;
-            for (int idx = gt; idx < nfull; idx += gthreads) {
-                uint4 v = ld_reuse(px4 + idx);
+            double vmaxd = 0.0;
+            if (k1_max) vmaxd = T.out_row[P.col_basic + kNBasic * T.slot + 10];
+            for (int idx = gt; idx < nfull && (MASKED || !k1_max); idx += gthreads) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (!k1_max) v = ld_reuse(px4 + idx);
                 if (MASKED) {
                     const uint2 m = __ldg(mk2 + idx);
                     const uint32_t c0 = __vcmpne4(m.x, 0u), c1 = __vcmpne4(m.y, 0u);
@@ -251,7 +308,8 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
                     const int i = nfull * 8 + k;
                     const bool ok = !MASKED || T.mk[i] != 0;
                     if (ok) {
-                        bits |= 1u << k; mx2 = __vmaxu2(mx2, (uint32_t)T.px[i]);
+                        bits |= 1u << k;
+                        if (!k1_max) mx2 = __vmaxu2(mx2, (uint32_t)T.px[i]);
                         const int ra = i / T.w, ca = i - ra * T.w;
                         brmin = min(brmin, ra); brmax = max(brmax, ra); bcmin = min(bcmin, ca); bcmax = max(bcmax, ca);
                     }
@@ -262,15 +320,20 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
                 brmin = __reduce_min_sync(0xffffffffu, brmin); brmax = __reduce_max_sync(0xffffffffu, brmax);
                 bcmin = __reduce_min_sync(0xffffffffu, bcmin); bcmax = __reduce_max_sync(0xffffffffu, bcmax);
                 if (lane == 0 && brmax >= 0) {
-                    atomicMin(&H.box[0], brmin); atomicMax(&H.box[1], brmax);
-                    atomicMin(&H.box[2], bcmin); atomicMax(&H.box[3], bcmax);
+                    atomicMin(&H.box[buf][0], brmin); atomicMax(&H.box[buf][1], brmax);
+                    atomicMin(&H.box[buf][2], bcmin); atomicMax(&H.box[buf][3], bcmax);
                 }
             }
-            const uint32_t wm = __reduce_max_sync(0xffffffffu, max(mx2 & 0xffffu, mx2 >> 16));
-            if (lane == 0) H.wmax[gw] = wm;
-            ring_group_sync(R);
-            uint32_t vmax = lane < R.gwarps ? H.wmax[lane] : 0u;
-            vmax = __reduce_max_sync(0xffffffffu, vmax);
+            uint32_t vmax;
+            if (k1_max) {
+                vmax = (vmaxd == vmaxd) ? (uint32_t)vmaxd : 0u;      // NaN: empty mask, no pair exists anyway
+            } else {
+                const uint32_t wm = __reduce_max_sync(0xffffffffu, max(mx2 & 0xffffu, mx2 >> 16));
+                if (lane == 0) H.wmax[gw] = wm;
+                ring_group_sync(R);
+                vmax = lane < R.gwarps ? H.wmax[lane] : 0u;
+                vmax = __reduce_max_sync(0xffffffffu, vmax);
+            }
 
             // ---- 2. quantise to 8 bits into shared memory ----
             uint32_t mul = 0, sh = 24;
@@ -294,13 +357,14 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
                 const int i = nfull * 8 + gt;
                 reinterpret_cast<uint8_t*>(Gp.q8)[i] = (uint8_t)min(k3_quant(T.px[i], mul, sh), 255u);
             }
-            ring_group_sync(R);
         }
+        ring_group_sync(R);                                // this tile staged; the previous one is complete
+        deferred_epilogue(buf ^ 1);
 
         // ---- 3. one GLCM per direction ----
         // box of pixels that can take part in a pair: the tile, or the mask's bounding box
         int bx[4] = {0, T.h - 1, 0, T.w - 1};
-        if (MASKED && active) { bx[0] = H.box[0]; bx[1] = H.box[1]; bx[2] = H.box[2]; bx[3] = H.box[3]; }
+        if (MASKED && active) { bx[0] = H.box[buf][0]; bx[1] = H.box[buf][1]; bx[2] = H.box[buf][2]; bx[3] = H.box[buf][3]; }
         for (int a = 0; a < P.n_angles; ++a) {
             const K3Geom G = k3_geom(T.w, P.dr[a], P.dc[a], bx[0], bx[1], bx[2], bx[3]);
             uint32_t I4[kK3Cache], J4[kK3Cache], vm[kK3Cache];
@@ -326,9 +390,9 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
                 const unsigned long long hf = warp_sum_redux((unsigned long long)__double2ll_rn(A.hom * 1099511627776.0));
                 if (lane == 0) {
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) atomicAdd(&H.acc[a][k], red[k]);
-                    atomicAdd(&H.acc[a][7], mm);
-                    H.whom[a][gw] = hf;
+                    for (int k = 0; k < 6; ++k) atomicAdd(&H.acc[buf][a][k], red[k]);
+                    atomicAdd(&H.acc[buf][a][7], mm);
+                    H.whom[buf][a][gw] = hf;
                 }
             }
             ring_acquire(R);                               // ---- table owned by this group ----
@@ -360,52 +424,20 @@ __global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant_
                 }
                 ring_release(R);                           // ---- hand the table to the next group ----
                 sold = __reduce_add_sync(0xffffffffu, sold);
-                if (lane == 0) atomicAdd(&H.acc[a][6], sold);
+                if (lane == 0) atomicAdd(&H.acc[buf][a][6], sold);
             } else {
                 ring_release(R);
             }
         }
 
-        // ---- 4. epilogue: one lane per direction ----
+        // ---- 4. the epilogue is deferred to the next round (after its staging barrier) ----
+        prev_active = active;
         if (active) {
-            ring_group_sync(R);                            // accumulators complete
-            // everyone read the mask box long ago; reset it before the next tile's stage 1 (one more
-            // group barrier follows below)
-            if (MASKED && gt == 32) { H.box[0] = 1 << 30; H.box[1] = -1; H.box[2] = 1 << 30; H.box[3] = -1; }
-            if (gw == 0 && lane < P.n_angles) {
-                const int a = lane;
-                const uint32_t* s = H.acc[a];
-                const long long M = (long long)s[7];
-                // non-existent pairs that went through the branch-free path (unmasked only)
-                const K3Geom Ge = k3_geom(T.w, P.dr[a], P.dc[a], 0, T.h - 1, 0, T.w - 1);
-                const long long D = MASKED ? 0ll : 4ll * Ge.nrows * Ge.gpr - M;
-                const unsigned long long sold_true = (unsigned long long)s[6] - (unsigned long long)(D * (D - 1) / 2);
-                unsigned long long hom_sum = 0ull;
-                for (int w = 0; w < R.gwarps; ++w) hom_sum += H.whom[a][w];
-                const unsigned long long hom_true = hom_sum - ((unsigned long long)D << 40);
-                double* o = T.out_row + P.col_glcm + (T.slot * P.n_angles + a) * kNGlcm;
-                if (M == 0) {
-                    o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 0.0; o[4] = 0.0; o[5] = 1.0;
-                    if (T.status) atomicOr(T.status, kStNoPairs);
-                } else {
-                    const double Md = (double)M;
-                    const long long con = (long long)s[2] + (long long)s[3] - 2ll * (long long)s[4];
-                    const long long vi = M * (long long)s[2] - (long long)s[0] * (long long)s[0];
-                    const long long vj = M * (long long)s[3] - (long long)s[1] * (long long)s[1];
-                    const long long cov = M * (long long)s[4] - (long long)s[0] * (long long)s[1];
-                    const double asmv = (double)(2ull * sold_true + (unsigned long long)M) / (Md * Md);
-                    o[0] = (double)con / Md;
-                    o[1] = (double)s[5] / Md;
-                    o[2] = ((double)hom_true * 9.094947017729282e-13) / Md;
-                    o[3] = asmv;
-                    o[4] = sqrt(asmv);
-                    o[5] = (vi == 0 || vj == 0) ? 1.0 : (double)cov / (sqrt((double)vi) * sqrt((double)vj));
-                }
-            }
-            ring_group_sync(R);                            // accumulators consumed
-            if (gt < kMaxAngles * 8) H.acc[gt >> 3][gt & 7] = 0u;
+            prev_row = T.out_row; prev_status = T.status; prev_slot = T.slot; prev_h = T.h; prev_w = T.w;
         }
     }
+    ring_group_sync(R);                                    // last tile of this group complete
+    deferred_epilogue((int)(n_iter & 1) ^ 1);
 }
 
 }  // namespace imfeat
