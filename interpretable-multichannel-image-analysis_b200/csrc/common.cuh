@@ -28,6 +28,7 @@ struct Params {
     double* out;
     uint32_t* status;          // nullable
     const double* log2tab;     // log2(k), k = 0..kMaxPixels (k=0 -> 0)
+    unsigned int* sched;       // per-call work counters, one per kernel (dynamic tile scheduling)
     const unsigned long long* gfix;  // round(2^42 * ((k+1)*log2(k+1) - k*log2(k))), k < kMaxPixels
     uint32_t* counts;          // nullable: GLCM bin dump [tile][angle][65536]
     long long n_tiles;
@@ -88,6 +89,16 @@ struct TileWalk {
     }
     __device__ __forceinline__ long long tile() const { return (long long)row * c_out + slot; }
 };
+
+// Dynamic tile scheduler of the warp-per-tile kernels: every warp draws its next tile from a
+// per-launch global counter (one atomic per tile, fetched one tile ahead so its latency is hidden).
+// Unlike a static stride it needs no assumption about how many CTAs are resident at once -- e.g.
+// while an NCCL all-gather of the previous batch occupies part of the machine.
+__device__ __forceinline__ long long next_tile(unsigned int* counter) {
+    unsigned int t = 0;
+    if ((threadIdx.x & 31) == 0) t = atomicAdd(counter, 1u);
+    return (long long)__shfl_sync(0xffffffffu, t, 0);
+}
 
 // 128-bit streaming load: the tile is read once per kernel, keep it out of L1.
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {

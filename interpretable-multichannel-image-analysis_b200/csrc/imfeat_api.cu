@@ -21,13 +21,18 @@ static_assert(kNShape == IMFEAT_N_SHAPE && kNMoment == IMFEAT_N_MOMENT, "header 
 static_assert(kMaxPixels == IMFEAT_MAX_PIXELS && kMaxAngles == IMFEAT_MAX_ANGLES, "header mismatch");
 
 constexpr int kTimingSlots = 64;
+constexpr int kSchedSlots = 256;
+constexpr int kWlSlots = 8;
 
 struct imfeat_ctx {
     int device;
     int sm_count;
     int k1_bps[2], k4_bps[2], k2c_bps[2], k4w_bps[2];   // resident CTAs per SM (occupancy API), [masked]
+    unsigned int* d_sched;      // ring of kSchedSlots x 8 work counters (one slot per extract call)
+    unsigned int sched_head;
     uint32_t* d_worklist;       // [0] = count, [1..] = tile ids left to the full-range K2 kernel
-    size_t worklist_cap;
+    size_t worklist_cap;        // entries per ring slot
+    unsigned int wl_head;
     double* d_log2tab;
     unsigned long long* d_gfix;
     long long launches;
@@ -132,6 +137,7 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
         const long double b = k ? (long double)k * log2l((long double)k) : 0.0L;
         gfix[k] = (unsigned long long)llroundl((a - b) * 4398046511104.0L);
     }
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_sched, sizeof(unsigned int) * 8 * kSchedSlots);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_gfix, sizeof(unsigned long long) * kMaxPixels);
     if (e == cudaSuccess)
         e = cudaMemcpy(ctx->d_gfix, gfix, sizeof(unsigned long long) * kMaxPixels, cudaMemcpyHostToDevice);
@@ -189,6 +195,7 @@ int imfeat_destroy(imfeat_ctx* ctx) {
     if (ctx->d_log2tab) cudaFree(ctx->d_log2tab);
     if (ctx->d_gfix) cudaFree(ctx->d_gfix);
     if (ctx->d_worklist) cudaFree(ctx->d_worklist);
+    if (ctx->d_sched) cudaFree(ctx->d_sched);
     free(ctx);
     return IMFEAT_OK;
 }
@@ -291,8 +298,13 @@ static int timing_resolve(imfeat_ctx* ctx, int slot) {
     return IMFEAT_OK;
 }
 
-static int launch_all(imfeat_ctx* ctx, const Params& P, const imfeat_opts* o, cudaStream_t st) {
-    if (P.n_tiles == 0) return IMFEAT_OK;
+static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o, cudaStream_t st) {
+    if (P_in.n_tiles == 0) return IMFEAT_OK;
+    Params P = P_in;
+    // work counters of this call's dynamically scheduled kernels (ring: calls on different streams
+    // may be in flight at the same time)
+    P.sched = ctx->d_sched + 8 * (ctx->sched_head++ % kSchedSlots);
+    CU(cudaMemsetAsync(P.sched, 0, sizeof(unsigned int) * 8, st));
     int slot = -1;
     if (ctx->timing) {
         slot = ctx->t_head;
@@ -337,20 +349,24 @@ static int launch_all(imfeat_ctx* ctx, const Params& P, const imfeat_opts* o, cu
         } else {
             // compact kernel first (value range < 4096, known from K1's min/max); it appends the
             // remaining tiles to a worklist that the full-range ring kernel then works off
+            // the worklist lives in a ring of kWlSlots buffers: calls on different streams (e.g. the two
+            // streams of the host pipeline) may be in flight at the same time
             if ((size_t)P.n_tiles + 1 > ctx->worklist_cap) {
+                CU(cudaDeviceSynchronize());               // rare: the batch grew; nobody may still use the old buffers
                 if (ctx->d_worklist) CU(cudaFree(ctx->d_worklist));
                 ctx->d_worklist = nullptr;
                 ctx->worklist_cap = 0;
-                CU(cudaMalloc((void**)&ctx->d_worklist, sizeof(uint32_t) * ((size_t)P.n_tiles + 1)));
+                CU(cudaMalloc((void**)&ctx->d_worklist, sizeof(uint32_t) * kWlSlots * ((size_t)P.n_tiles + 1)));
                 ctx->worklist_cap = (size_t)P.n_tiles + 1;
             }
-            CU(cudaMemsetAsync(ctx->d_worklist, 0, sizeof(uint32_t), st));
+            uint32_t* wl = ctx->d_worklist + (size_t)(ctx->wl_head++ % kWlSlots) * ctx->worklist_cap;
+            CU(cudaMemsetAsync(wl, 0, sizeof(uint32_t), st));
             const long long resc = sm * (ctx->k2c_bps[masked] > 0 ? ctx->k2c_bps[masked] : 1);
             const int gc = (int)(P.n_tiles < resc ? P.n_tiles : resc);
-            if (masked) k2c_order_entropy_kernel<true><<<gc, kK2cThreads, 0, st>>>(P, ctx->d_worklist + 1, ctx->d_worklist);
-            else k2c_order_entropy_kernel<false><<<gc, kK2cThreads, 0, st>>>(P, ctx->d_worklist + 1, ctx->d_worklist);
-            if (masked) k2_order_entropy_kernel<true><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, ctx->d_worklist + 1, ctx->d_worklist);
-            else k2_order_entropy_kernel<false><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, ctx->d_worklist + 1, ctx->d_worklist);
+            if (masked) k2c_order_entropy_kernel<true><<<gc, kK2cThreads, 0, st>>>(P, wl + 1, wl);
+            else k2c_order_entropy_kernel<false><<<gc, kK2cThreads, 0, st>>>(P, wl + 1, wl);
+            if (masked) k2_order_entropy_kernel<true><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, wl + 1, wl);
+            else k2_order_entropy_kernel<false><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, wl + 1, wl);
             ctx->launches += 3;
         }
         IMFEAT_MARK(1)

@@ -118,10 +118,12 @@ __global__ void __launch_bounds__(256) k1_moments_kernel(const __grid_constant__
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
 
-    TileWalk walk;
-    walk.init(P, warp0 < P.n_tiles ? warp0 : 0, nwarps);
-    for (long long t = warp0; t < P.n_tiles; t += nwarps, walk.next()) {
-        const Tile T = resolve_tile_rs(P, walk.row, walk.slot);
+    (void)warp0; (void)nwarps;
+    long long tnext = next_tile(P.sched + 0);
+    while (tnext < P.n_tiles) {
+        const long long t = tnext;
+        tnext = next_tile(P.sched + 0);                    // one tile ahead
+        const Tile T = resolve_tile(P, t);
         const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
         const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
         const int nfull = T.n >> 3, rem = T.n & 7;

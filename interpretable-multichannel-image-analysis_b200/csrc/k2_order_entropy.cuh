@@ -423,10 +423,12 @@ __global__ void __launch_bounds__(kK2cThreads, 24) k2c_order_entropy_kernel(cons
     if (tid == 0) { S.cnt = 0u; S.constant = 0; }
     __syncthreads();
 
-    TileWalk walk;
-    walk.init(P, blockIdx.x < P.n_tiles ? blockIdx.x : 0, gridDim.x);
-    for (long long t = blockIdx.x; t < P.n_tiles; t += gridDim.x, walk.next()) {
-        const Tile T = resolve_tile_rs(P, walk.row, walk.slot);
+    static_assert(kK2cThreads == 32, "the dynamic scheduler below assumes one warp per CTA");
+    long long tnext = next_tile(P.sched + 1);
+    while (tnext < P.n_tiles) {
+        const long long t = tnext;
+        tnext = next_tile(P.sched + 1);                      // one tile ahead
+        const Tile T = resolve_tile(P, t);
         double* o = T.out_row + P.col_basic + kNBasic * T.slot;
         const double dmin = o[0], dmax = o[10];              // written by K1 (earlier launch, same stream)
         if (!(dmin == dmin)) {                               // NaN: no pixel inside the mask

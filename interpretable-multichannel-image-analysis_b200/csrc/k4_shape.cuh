@@ -379,10 +379,11 @@ __global__ void __launch_bounds__(32, 20) k4w_shape_kernel(const __grid_constant
     const int lane = threadIdx.x;
     const bool want_mom = P.col_moment >= 0;
 
-    TileWalk walk;
-    walk.init(P, blockIdx.x < P.n_tiles ? blockIdx.x : 0, gridDim.x);
-    for (long long t = blockIdx.x; t < P.n_tiles; t += gridDim.x, walk.next()) {
-        const Tile T = resolve_tile_rs(P, walk.row, walk.slot);
+    long long tnext = next_tile(P.sched + 3);
+    while (tnext < P.n_tiles) {
+        const long long t = tnext;
+        tnext = next_tile(P.sched + 3);                    // one tile ahead
+        const Tile T = resolve_tile(P, t);
         const int h = T.h, w = T.w;
         const int Pw = (w + 31) >> 5;
         int rmin = 1 << 30, rmax = -1, cmin = 1 << 30, cmax = -1;

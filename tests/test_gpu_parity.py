@@ -393,3 +393,21 @@ def test_pinned_batcher_end_to_end(torch_mod):
     for k, (img, m) in enumerate(objs):
         want = c_oracle.table(_planar(img[None]), _planar(m[None].astype(np.uint8)))
         compare_tables(table[k:k + 1], want, cols, label="batcher %d" % k)
+
+
+def test_wide_range_tiles_through_host_pipeline(torch_mod):
+    """Full 16-bit data (value range >= 4096) takes the worklist path K2c -> K2; 1,400 objects go
+    through the two-stream host pipeline, so two worklists are in flight at once."""
+    rng = np.random.default_rng(33)
+    n = 1400
+    img = rng.integers(0, 65536, (n, 64, 64, 12)).astype(np.uint16)
+    img[::3] = rng.integers(0, 4096, (len(img[::3]), 64, 64, 12)).astype(np.uint16)   # mixed: some tiles stay compact
+    ex = imf.get_extractor(glcm=False)
+    got = ex.extract_host_hwc(img)
+    pick = rng.choice(n, 40, replace=False)
+    want = c_oracle.table(_planar(img[pick]), glcm=False)
+    compare_tables(got[pick], want, imf.feature_columns(12, glcm=False), label="wide range")
+    import torch
+    planes = torch.from_numpy(_planar(img)).cuda()
+    dev = ex.extract_planar(planes).cpu().numpy()
+    assert np.array_equal(got, dev, equal_nan=True)
