@@ -12,6 +12,7 @@
 #include "k1_moments.cuh"
 #include "k2_order_entropy.cuh"
 #include "k3_glcm.cuh"
+#include "k3a_sums.cuh"
 #include "k4_shape.cuh"
 
 using namespace imfeat;
@@ -28,6 +29,8 @@ struct imfeat_ctx {
     int device;
     int sm_count;
     int k1_bps[2], k4_bps[2], k2c_bps[2], k4w_bps[2];   // resident CTAs per SM (occupancy API), [masked]
+    cudaMemPool_t pool;         // stream-ordered scratch (K3 records); keeps its memory between calls
+    int k3a_bps[2], k3a_maxpx;                          // same for K3a, valid for k3a_maxpx (dynamic smem)
     unsigned int* d_sched;      // ring of kSchedSlots x 8 work counters (one slot per extract call)
     unsigned int sched_head;
     uint32_t* d_worklist;       // [0] = count, [1..] = tile ids left to the full-range K2 kernel
@@ -138,16 +141,30 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
         gfix[k] = (unsigned long long)llroundl((a - b) * 4398046511104.0L);
     }
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_sched, sizeof(unsigned int) * 8 * kSchedSlots);
+    if (e == cudaSuccess) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        e = cudaMemPoolCreate(&ctx->pool, &props);
+        unsigned long long keep = ~0ull;
+        if (e == cudaSuccess) e = cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_gfix, sizeof(unsigned long long) * kMaxPixels);
     if (e == cudaSuccess)
         e = cudaMemcpy(ctx->d_gfix, gfix, sizeof(unsigned long long) * kMaxPixels, cudaMemcpyHostToDevice);
     free(tab);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_order_entropy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_order_entropy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k4_shape_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k4_shape_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_moments_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -196,20 +213,23 @@ int imfeat_destroy(imfeat_ctx* ctx) {
     if (ctx->d_gfix) cudaFree(ctx->d_gfix);
     if (ctx->d_worklist) cudaFree(ctx->d_worklist);
     if (ctx->d_sched) cudaFree(ctx->d_sched);
+    if (ctx->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(ctx->pool); }
     free(ctx);
     return IMFEAT_OK;
 }
 
 }  // extern "C"
 
-// Number of thread groups sharing the GLCM table: more groups = more tiles in flight and less fixed
-// per-thread overhead per pair, limited by the per-group staging of the quantised tile.
-static int k3_groups(int max_pixels) {
-    const char* env = getenv("IMFEAT_K3_GROUPS");
-    int want = env ? atoi(env) : 4;
-    if (want != 2 && want != 4 && want != 8) want = 4;
-    while (want > 2 && k3_smem_bytes(max_pixels, want) > 220 * 1024) want /= 2;
-    return want;
+template <bool DUMP>
+static void launch_k3(bool masked, int ng, int grid, size_t smem, cudaStream_t st, const Params& P,
+                      const unsigned char* recs, int maxpx, int ns) {
+    if (ng == 4) {
+        if (masked) k3_glcm_kernel<true, DUMP, 4><<<grid, kK3Threads, smem, st>>>(P, recs, maxpx, ns);
+        else k3_glcm_kernel<false, DUMP, 4><<<grid, kK3Threads, smem, st>>>(P, recs, maxpx, ns);
+    } else {
+        if (masked) k3_glcm_kernel<true, DUMP, 2><<<grid, kK3Threads, smem, st>>>(P, recs, maxpx, ns);
+        else k3_glcm_kernel<false, DUMP, 2><<<grid, kK3Threads, smem, st>>>(P, recs, maxpx, ns);
+    }
 }
 
 // K2: measured on B200 (10,000 64x64x12 objects): unmasked 1.59 ms with 4 groups vs 1.84 ms with 2;
@@ -374,11 +394,26 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
     if (o->want_glcm) {
         const int g3 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
         const int maxpx = ((P.hs * P.ws + 7) & ~7);
-        const int ng3 = k3_groups(maxpx);
-        if (masked) k3_glcm_kernel<true, false><<<g3, 1024, k3_smem_bytes(maxpx, ng3), st>>>(P, ng3, maxpx);
-        else k3_glcm_kernel<false, false><<<g3, 1024, k3_smem_bytes(maxpx, ng3), st>>>(P, ng3, maxpx);
+        // K3a: quantise; contrast, dissimilarity, homogeneity, correlation straight from the pair stream
+        // (warp per tile); leaves one record per tile for K3 in a stream-ordered scratch buffer
+        const size_t smem_a = k3a_smem_bytes(maxpx, masked);
+        if (ctx->k3a_maxpx != maxpx) {
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k3a_bps[0], k3a_glcm_sums_kernel<false>, kK3aThreads, k3a_smem_bytes(maxpx, false)));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k3a_bps[1], k3a_glcm_sums_kernel<true>, kK3aThreads, k3a_smem_bytes(maxpx, true)));
+            ctx->k3a_maxpx = maxpx;
+        }
+        unsigned char* recs = nullptr;
+        CU(cudaMallocFromPoolAsync((void**)&recs, k3_rec_bytes(maxpx, masked) * (size_t)P.n_tiles, ctx->pool, st));
+        const long long resa = sm * (ctx->k3a_bps[masked] > 0 ? ctx->k3a_bps[masked] : 1);
+        const int ga = (int)(P.n_tiles < resa ? P.n_tiles : resa);
+        if (masked) k3a_glcm_sums_kernel<true><<<ga, kK3aThreads, smem_a, st>>>(P, recs, maxpx);
+        else k3a_glcm_sums_kernel<false><<<ga, kK3aThreads, smem_a, st>>>(P, recs, maxpx);
+        // K3: the bins (ASM, energy) on the shared-memory table, two groups taking turns
+        const int ns3 = k3_stages(maxpx, masked);
+        launch_k3<false>(masked, k3_groups(maxpx, masked), g3, k3_smem_bytes(maxpx, masked), st, P, recs, maxpx, ns3);
+        CU(cudaFreeAsync(recs, st));
         IMFEAT_MARK(2)
-        ctx->launches += 1;
+        ctx->launches += 2;
     }
     if (o->want_shape || o->want_moments) {
         const char* k4env = getenv("IMFEAT_K4_WARP");
@@ -474,9 +509,19 @@ int imfeat_glcm_counts_device(imfeat_ctx* ctx, const uint16_t* d_planes, const u
     P.counts = d_counts;
     const int g3 = (int)(P.n_tiles < ctx->sm_count ? P.n_tiles : ctx->sm_count);
     const int maxpx = ((P.hs * P.ws + 7) & ~7);
-    const int ng3 = k3_groups(maxpx);
-    if (d_masks) k3_glcm_kernel<true, true><<<g3, 1024, k3_smem_bytes(maxpx, ng3), st>>>(P, ng3, maxpx);
-    else k3_glcm_kernel<false, true><<<g3, 1024, k3_smem_bytes(maxpx, ng3), st>>>(P, ng3, maxpx);
+    const bool masked = d_masks != nullptr;
+    unsigned int* sched = ctx->d_sched + (size_t)(ctx->sched_head++ % kSchedSlots) * 8;
+    CU(cudaMemsetAsync(sched, 0, sizeof(unsigned int) * 8, st));
+    P.sched = sched;
+    unsigned char* recs = nullptr;
+    CU(cudaMallocFromPoolAsync((void**)&recs, k3_rec_bytes(maxpx, masked) * (size_t)P.n_tiles, ctx->pool, st));
+    const int ga = (int)(P.n_tiles < 16ll * ctx->sm_count ? P.n_tiles : 16ll * ctx->sm_count);
+    if (masked) k3a_glcm_sums_kernel<true><<<ga, kK3aThreads, k3a_smem_bytes(maxpx, true), st>>>(P, recs, maxpx);
+    else k3a_glcm_sums_kernel<false><<<ga, kK3aThreads, k3a_smem_bytes(maxpx, false), st>>>(P, recs, maxpx);
+    const int ns3 = k3_stages(maxpx, masked);
+    launch_k3<true>(masked, k3_groups(maxpx, masked), g3, k3_smem_bytes(maxpx, masked), st, P, recs, maxpx, ns3);
+    CU(cudaFreeAsync(recs, st));
+    ctx->launches += 1;
     ctx->launches += 1;
     CU(cudaGetLastError());
     CU(cudaFreeAsync(scratch, st));

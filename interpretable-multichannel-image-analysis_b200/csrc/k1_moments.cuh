@@ -235,31 +235,6 @@ namespace imfeat {
 constexpr int kK1TmaConsumers = 16;                 // consumer warps per CTA
 constexpr int kK1TmaThreads = 32 * (kK1TmaConsumers + 1);
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-        "@!p bra WAIT_%=;\n"
-        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
 __global__ void __launch_bounds__(kK1TmaThreads, 1)
 k1_moments_tma_kernel(const __grid_constant__ Params P, int n_stages, int stage_bytes) {
     extern __shared__ __align__(128) unsigned char k1_smem[];

@@ -7,51 +7,62 @@
 //
 // * quantiser: floor(255*x/max) with an exact multiply-shift reciprocal (bit-identical to the
 //   notebook's float64 expression for every uint16 pair; tests/test_oracle_cpu.py).
-// * the 256x256 bins live in shared memory as 16-bit counters (two per 32-bit word, 128 KB),
-//   built with shared-memory atomics on the pair stream, dumped on request (parity), and only
-//   ever cleared sparsely by re-walking the pairs.  Two 512-thread groups work on two tiles at a
-//   time and take turns on the table (common.cuh, "ping-pong"); everything that does not need
-//   the table (loads, max, quantisation, pair-stream sums, reductions, epilogue) overlaps the
-//   other group's table phase.
-// * contrast / dissimilarity / correlation come from exact integer sums over the pair stream,
-//   four pairs per SIMD video instruction (dp4a, vabsdiff4); ASM = sum_bins c^2 is accumulated
-//   from the atomics' return values (c^2 = sum_{k<c} (2k+1) = 2*sum(old) + c), so there is no
-//   pass over the bins and no read-back pass.
+// * the work is split over two kernels.  K3a (k3a_sums.cuh, one warp per tile) quantises the tile,
+//   computes the four properties that are linear in the matrix straight from the pair stream and
+//   leaves a per-tile record (header, quantised bytes, mask bits) in a scratch buffer.  K3 (this
+//   file) only builds the bins, for ASM and energy.
+// * the 256x256 bins live in shared memory as 16-bit counters (two per 32-bit word, 128 KB), built
+//   with shared-memory atomics on the pair stream, dumped on request (parity), and only ever
+//   cleared sparsely by re-walking the pairs.  One persistent CTA per SM; its two 512-thread groups
+//   work on two tiles at a time and take turns on the table, handing it over with named barriers
+//   (bar.arrive / bar.sync: the waiting group is parked in hardware and issues nothing).  While one
+//   group owns the table the other loads the pair items of its next direction into registers.
+// * records arrive through a shared-memory ring filled by cp.async.bulk (1-D TMA) completing on
+//   mbarriers, several tiles ahead, so staging costs no instructions.
+// * ASM = sum_bins c^2 is accumulated from the atomics' return values
+//   (c^2 = sum_{k<c} (2k+1) = 2*sum(old) + c), so there is no pass over the bins.
 #pragma once
 #include "common.cuh"
 
 namespace imfeat {
 
 
-constexpr int kK3Cache = 4;     // pair groups (4 pairs each) per thread cached in registers
+constexpr int kK3Threads = 1024;     // NG groups of 1024 / NG threads
+constexpr int kK3MaxStages = 4;      // records in flight per group
 
-// Shared-memory layout (dynamic): [hist 128 KB][homtab 2 KB][tokens][per-group: K3GroupHdr, q8, mbits]
-struct K3GroupHdr {
-    // per-tile scratch exists twice and alternates: a tile's epilogue runs while the next tile is
-    // already under way (after that tile's staging barrier), so no barrier is spent on it
-    unsigned long long whom[2][kMaxAngles][16];   // per-warp sums of 1/(1+d^2) in 2^-40 fixed point
-    uint32_t acc[2][kMaxAngles][8];               // si sj sii sjj sij sd sold m, per direction
-    int box[2][4];                                // mask bounding box: rmin, rmax, cmin, cmax (masked variant)
-    uint32_t wmax[32];
+// Per-tile record written by K3a and consumed by K3: 32-byte header, quantised pixels (one byte each,
+// row-major, + slack for unaligned 4-byte reads), mask bits (masked variant only).
+struct K3RecHdr {
+    int box[4];                      // rows [box0, box1], columns [box2, box3] that can hold pairs
+    int h, w, pad[2];
 };
+__host__ __device__ inline int k3_q8_words(int max_pixels) { return (max_pixels / 4 + 4 + 3) & ~3; }
+__host__ __device__ inline int k3_mb_words(int max_pixels, bool masked) { return masked ? ((max_pixels / 32 + 2 + 3) & ~3) : 0; }
+__host__ __device__ inline size_t k3_rec_bytes(int max_pixels, bool masked) {
+    return sizeof(K3RecHdr) + 4 * (size_t)(k3_q8_words(max_pixels) + k3_mb_words(max_pixels, masked));
+}
+
 struct K3Smem {
     uint32_t hist[32768];
-    uint32_t dummy[34];      // at hist + 0x20000: word 0 takes the non-existent pairs of the unmasked path,
-                             // words 2..33 (one per lane) those of the masked path
-    double homtab[256];
-    unsigned long long tokens[8];
+    uint32_t dummy[kK3Threads];                 // at hist + 0x20000: one word per thread for its non-existent pairs
+    unsigned long long full[4][kK3MaxStages];   // mbarriers: record landed
+    uint32_t acc[4][kMaxAngles][2];             // per group and direction: sum of returned old counts, pair count
 };
-struct K3Group {                               // pointers into the dynamic region of this group
-    K3GroupHdr* hdr;
+struct K3Group {                               // where the quantised tile and its mask bits live
     uint32_t* q8;                              // quantised pixels (bytes) + slack for unaligned reads
     uint32_t* mbits;                           // one bit per pixel: inside the mask (masked variant)
 };
-__host__ __device__ inline size_t k3_group_bytes(int max_pixels) {
-    const size_t q8w = (size_t)max_pixels / 4 + 4, mbw = (size_t)max_pixels / 32 + 2;
-    return sizeof(K3GroupHdr) + 4 * ((q8w + 1) & ~(size_t)1) + 4 * ((mbw + 1) & ~(size_t)1);
+// groups sharing the table (4, or 2 when the records are too large for four rings) and ring depth
+__host__ __device__ inline int k3_groups(int max_pixels, bool masked) {
+    return 4 * k3_rec_bytes(max_pixels, masked) <= 227 * 1024 - sizeof(K3Smem) ? 4 : 2;
 }
-__host__ __device__ inline size_t k3_smem_bytes(int max_pixels, int ng) {
-    return sizeof(K3Smem) + (size_t)ng * k3_group_bytes(max_pixels);
+__host__ __device__ inline int k3_stages(int max_pixels, bool masked) {
+    const size_t room = 227 * 1024 - sizeof(K3Smem);
+    const size_t ns = room / (k3_groups(max_pixels, masked) * k3_rec_bytes(max_pixels, masked));
+    return ns > (size_t)kK3MaxStages ? kK3MaxStages : (int)ns;
+}
+__host__ __device__ inline size_t k3_smem_bytes(int max_pixels, bool masked) {
+    return sizeof(K3Smem) + (size_t)k3_groups(max_pixels, masked) * k3_stages(max_pixels, masked) * k3_rec_bytes(max_pixels, masked);
 }
 
 struct K3Acc {
@@ -129,7 +140,7 @@ __device__ __forceinline__ bool k3_item(const K3Group& Gp, const K3Geom& G, int 
 // (row tails) are zero, so they add nothing to the integer sums and exactly homtab[0] = 1.0 to the
 // homogeneity sum, which the epilogue subtracts again.
 template <bool MASKED>
-__device__ __forceinline__ void k3_sums(const K3Smem& S, uint32_t I4, uint32_t J4, uint32_t vm, K3Acc& A) {
+__device__ __forceinline__ void k3_sums(const double* homtab, uint32_t I4, uint32_t J4, uint32_t vm, K3Acc& A) {
     A.si = __dp4a(I4, 0x01010101u, A.si);
     A.sj = __dp4a(J4, 0x01010101u, A.sj);
     A.sii = __dp4a(I4, I4, A.sii);
@@ -138,306 +149,203 @@ __device__ __forceinline__ void k3_sums(const K3Smem& S, uint32_t I4, uint32_t J
     A.sd += __vsadu4(I4, J4);
     A.m += __popc(vm) >> 3;
     const uint32_t D4 = __vabsdiffu4(I4, J4);
-    A.hom += S.homtab[D4 & 0xffu];
-    A.hom += S.homtab[(D4 >> 8) & 0xffu];
-    A.hom += S.homtab[(D4 >> 16) & 0xffu];
-    A.hom += S.homtab[D4 >> 24];
+    A.hom += homtab[D4 & 0xffu];
+    A.hom += homtab[(D4 >> 8) & 0xffu];
+    A.hom += homtab[(D4 >> 16) & 0xffu];
+    A.hom += homtab[D4 >> 24];
     // masked tiles: take the 1.0 of every missing pair out again right away (exact)
     if (MASKED) A.hom -= (double)(4 - (__popc(vm) >> 3));
 }
 
-// PHASE 0: bins += 1, accumulating the returned old counts (sum_bins c^2 = 2*sum(old) + M);
-// PHASE 2: sparse clear.  Keys (i << 8 | j) are assembled two at a time with PRMT.
-// Both variants run branch-free.  Unmasked: a non-existent pair (row tail) is redirected to one
-// dummy bin behind the table; D such pairs return the old values 0..D-1 in some order, so the
-// epilogue subtracts D(D-1)/2.  Masked (many missing pairs): each lane has its own dummy word and
-// the returned count of a missing pair is dropped with a select.
-template <int PHASE, bool MASKED>
-__device__ __forceinline__ void k3_bin1(K3Smem& S, uint32_t key, bool exists, uint32_t& sold) {
-    uint32_t off = (key << 1) & 0x1fffcu;
-    off = exists ? off : (MASKED ? 0x20008u + 4u * (threadIdx.x & 31) : 0x20000u);
-    uint32_t* word = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(S.hist) + off);
-    if (PHASE == 0) {
-        const uint32_t sh = (key & 1u) << 4;       // key == 0 for a non-existent pair
-        const uint32_t old = (atomicAdd(word, 1u << sh) >> sh) & 0xffffu;
-        sold += (MASKED && !exists) ? 0u : old;    // unmasked: corrected by D(D-1)/2 in the epilogue
-    } else {
-        *word = 0u;
-    }
-}
-template <int PHASE, bool MASKED>
-__device__ __forceinline__ void k3_bins(K3Smem& S, uint32_t I4, uint32_t J4, uint32_t vm, uint32_t& sold) {
-    const uint32_t K01 = __byte_perm(J4, I4, 0x5140);   // [j0, i0, j1, i1]
+// ---- the bins ------------------------------------------------------------------------------------
+// Bin (i, j) is a 16-bit counter: word (i << 7 | j >> 1) of the table, half j & 1.  A pair is turned
+// into a "hit" h = byte offset of the word | half (bit 0) while the group does not own the table; a
+// pair that does not exist (row tail, outside the mask) gets the thread's own dummy word behind the
+// table instead, so the table phase is branch-free: six instructions per pair,
+//   p = h & 1;  addr = h & ~3;  inc = 1 + p * 0xffff;  sel = 1 + p * 0xff;
+//   old = ATOMS.ADD [addr], inc;  sold = IDP.2A(old, sel) + sold        (adds the selected half)
+// sum_bins c^2 = 2 * sum(old) + M  (c^2 = sum_{k<c} (2k+1)), so the bins are never read back.  The d
+// dummy hits of a thread return 0..d-1: it subtracts d(d-1)/2 itself.  Clearing re-walks the hits.
+template <bool MASKED>
+__device__ __forceinline__ void k3_hits(uint32_t I4, uint32_t J4, uint32_t vm, uint32_t dummy_off, uint32_t (&h)[4]) {
+    const uint32_t K01 = __byte_perm(J4, I4, 0x5140);   // [j0, i0, j1, i1]: keys i << 8 | j
     const uint32_t K23 = __byte_perm(J4, I4, 0x7362);   // [j2, i2, j3, i3]
-    k3_bin1<PHASE, MASKED>(S, K01 & 0xffffu, (vm & 0x00000001u) != 0u, sold);
-    k3_bin1<PHASE, MASKED>(S, K01 >> 16, (vm & 0x00000100u) != 0u, sold);
-    k3_bin1<PHASE, MASKED>(S, K23 & 0xffffu, (vm & 0x00010000u) != 0u, sold);
-    k3_bin1<PHASE, MASKED>(S, K23 >> 16, (vm & 0x01000000u) != 0u, sold);
+    h[0] = ((K01 << 1) & 0x1fffcu) | (K01 & 1u);
+    h[1] = ((K01 >> 15) & 0x1fffcu) | ((K01 >> 16) & 1u);
+    h[2] = ((K23 << 1) & 0x1fffcu) | (K23 & 1u);
+    h[3] = ((K23 >> 15) & 0x1fffcu) | ((K23 >> 16) & 1u);
+    h[0] = (vm & 0x000000ffu) ? h[0] : dummy_off;
+    h[1] = (vm & 0x0000ff00u) ? h[1] : dummy_off;
+    h[2] = (vm & 0x00ff0000u) ? h[2] : dummy_off;
+    h[3] = (vm & 0xff000000u) ? h[3] : dummy_off;
+}
+// increments the bin of hit h (leaving the word's byte offset in h) and accumulates the old count
+__device__ __forceinline__ void k3_hit(uint32_t hist_addr, uint32_t& h, uint32_t& sold) {
+    const uint32_t p = h & 1u;
+    h &= ~3u;
+    const uint32_t sel = p * 0xffu + 1u, inc = p * 0xffffu + 1u;
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(hist_addr + h), "r"(inc) : "memory");
+    sold = __dp2a_lo(old, sel, sold);
+}
+__device__ __forceinline__ void k3_unhit(uint32_t hist_addr, uint32_t h) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(hist_addr + (h & ~3u)), "r"(0u) : "memory");
 }
 
-// One direction's six properties from the exact integer sums (s: si sj sii sjj sij sd sold m).
-template <bool MASKED>
-__device__ __forceinline__ void k3_epilogue(const Params& P, double* out_row, uint32_t* status, int slot,
-                                            int h, int w, int a, const uint32_t* s, unsigned long long hom_sum) {
-    const long long M = (long long)s[7];
+// ASM and energy of one direction from sum(old) and the pair count (the other four properties are
+// written by k3a_glcm_sums_kernel).
+__device__ __forceinline__ void k3_epilogue(const Params& P, double* out_row, int slot, int a,
+                                            unsigned long long sold, long long M) {
     double* o = out_row + P.col_glcm + (slot * P.n_angles + a) * kNGlcm;
-    if (M == 0) {
-        o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 0.0; o[4] = 0.0; o[5] = 1.0;
-        if (status) atomicOr(status, kStNoPairs);
-        return;
-    }
-    // non-existent pairs that went through the branch-free path (unmasked only)
-    const K3Geom Ge = k3_geom(w, P.dr[a], P.dc[a], 0, h - 1, 0, w - 1);
-    const long long D = MASKED ? 0ll : 4ll * Ge.nrows * Ge.gpr - M;
-    const unsigned long long sold_true = (unsigned long long)s[6] - (unsigned long long)(D * (D - 1) / 2);
-    const unsigned long long hom_true = hom_sum - ((unsigned long long)D << 40);
+    if (M == 0) { o[3] = 0.0; o[4] = 0.0; return; }
     const double Md = (double)M;
-    const long long con = (long long)s[2] + (long long)s[3] - 2ll * (long long)s[4];
-    const long long vi = M * (long long)s[2] - (long long)s[0] * (long long)s[0];
-    const long long vj = M * (long long)s[3] - (long long)s[1] * (long long)s[1];
-    const long long cov = M * (long long)s[4] - (long long)s[0] * (long long)s[1];
-    const double asmv = (double)(2ull * sold_true + (unsigned long long)M) / (Md * Md);
-    o[0] = (double)con / Md;
-    o[1] = (double)s[5] / Md;
-    o[2] = ((double)hom_true * 9.094947017729282e-13) / Md;
+    const double asmv = (double)(2ull * sold + (unsigned long long)M) / (Md * Md);
     o[3] = asmv;
     o[4] = sqrt(asmv);
-    o[5] = (vi == 0 || vj == 0) ? 1.0 : (double)cov / (sqrt((double)vi) * sqrt((double)vj));
 }
 
-template <bool MASKED, bool DUMP>
-__global__ void __launch_bounds__(1024, 1) k3_glcm_kernel(const __grid_constant__ Params P, int ng, int max_pixels) {
+template <bool MASKED, bool DUMP, int NG>
+__global__ void __launch_bounds__(kK3Threads, 1)
+k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict__ recs, int max_pixels, int ns) {
     extern __shared__ __align__(16) unsigned char k3_smem_raw[];
     K3Smem& S = *reinterpret_cast<K3Smem*>(k3_smem_raw);
+    constexpr int gthreads = kK3Threads / NG;
+    constexpr int kCache = 1024 / gthreads;                // items (4 pairs each) per thread held in registers
     const int tid = threadIdx.x, lane = tid & 31;
-    Ring R;
-    ring_init(R, S.tokens, ng);
-    const int g = R.g, gt = R.gt, gw = R.gw, gthreads = R.gthreads;
-    K3Group Gp;
-    {
-        unsigned char* base = k3_smem_raw + sizeof(K3Smem) + (size_t)g * k3_group_bytes(max_pixels);
-        const size_t q8w = ((size_t)max_pixels / 4 + 4 + 1) & ~(size_t)1;
-        Gp.hdr = reinterpret_cast<K3GroupHdr*>(base);
-        Gp.q8 = reinterpret_cast<uint32_t*>(base + sizeof(K3GroupHdr));
-        Gp.mbits = Gp.q8 + q8w;
+    const int g = tid / gthreads, gt = tid % gthreads, gw = gt >> 5;
+    const uint32_t rec_bytes = (uint32_t)k3_rec_bytes(max_pixels, MASKED);
+    const int q8w = k3_q8_words(max_pixels);
+    unsigned char* stage0 = k3_smem_raw + sizeof(K3Smem) + (size_t)g * ns * rec_bytes;
+    const uint32_t full0 = smem_addr(&S.full[g][0]);
+    const uint32_t hist_addr = smem_addr(S.hist);
+    const uint32_t dummy_off = 0x20000u + 4u * (uint32_t)tid;
+    const int id_sync = 1 + g, id_mine = 1 + NG + g, id_next = 1 + NG + (g + 1) % NG;
+
+    for (int k = tid; k < 32768; k += kK3Threads) S.hist[k] = 0u;
+    S.dummy[tid] = 0u;
+    if (tid < 4 * kMaxAngles * 2) (&S.acc[0][0][0])[tid] = 0u;
+    if (tid == 0) {
+        for (int i = 0; i < 4 * kK3MaxStages; ++i) mbar_init(smem_addr(&S.full[0][0]) + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    K3GroupHdr& H = *Gp.hdr;
-
-    for (int k = tid; k < 32768; k += blockDim.x) S.hist[k] = 0u;
-    if (tid < 256) S.homtab[tid] = 1.0 / (1.0 + (double)(tid * tid));
-    if (tid < 34) S.dummy[tid] = 0u;
-    if (gt < 2) { H.box[gt][0] = 1 << 30; H.box[gt][1] = -1; H.box[gt][2] = 1 << 30; H.box[gt][3] = -1; }
-    if (gt < 2 * kMaxAngles * 8) (&H.acc[0][0][0])[gt] = 0u;
     __syncthreads();
-    // K1 (same stream, earlier launch) already wrote the tile maximum into the table when the basic
-    // block is requested; then the max pass and its barrier are skipped.
-    const bool k1_max = P.col_basic >= 0;
-    // deferred epilogue of this group's previous tile
-    bool prev_active = false;
-    double* prev_row = nullptr;
-    uint32_t* prev_status = nullptr;
-    int prev_slot = 0, prev_h = 0, prev_w = 0;
-    auto deferred_epilogue = [&](int pbuf) {
-        if (prev_active && gw < P.n_angles && lane == 0) {
-            unsigned long long hom_sum = 0ull;
-            for (int w = 0; w < R.gwarps; ++w) hom_sum += H.whom[pbuf][gw][w];
-            k3_epilogue<MASKED>(P, prev_row, prev_status, prev_slot, prev_h, prev_w, gw, H.acc[pbuf][gw], hom_sum);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) H.acc[pbuf][gw][k] = 0u;
-        }
-        if (MASKED && prev_active && gt == 0) {
-            H.box[pbuf][0] = 1 << 30; H.box[pbuf][1] = -1; H.box[pbuf][2] = 1 << 30; H.box[pbuf][3] = -1;
-        }
-        prev_active = false;
+
+    // tiles of this CTA: blockIdx.x + k * gridDim.x; group g takes k = NG * j + g
+    const uint32_t n_tiles = (uint32_t)P.n_tiles, first = blockIdx.x;
+    const uint32_t mine = first < n_tiles ? (n_tiles - first + gridDim.x - 1) / gridDim.x : 0u;
+    const uint32_t n_iter = (mine + NG - 1) / NG;          // every group runs the same number of rounds
+    const uint32_t my_count = (mine + NG - 1 - g) / NG;
+    const uint32_t t_step = NG * gridDim.x;
+    auto fetch = [&](uint32_t tile, int s) {               // one thread: start the bulk copy of a record
+        mbar_expect_tx(full0 + 8 * s, rec_bytes);
+        bulk_g2s(smem_addr(stage0 + (size_t)s * rec_bytes), recs + (size_t)tile * rec_bytes, rec_bytes, full0 + 8 * s);
     };
+    uint32_t t = first + g * gridDim.x;                    // this round's tile
+    if (gt == 0) {
+        for (uint32_t j = 0; j < (uint32_t)ns && j < my_count; ++j) fetch(t + j * t_step, (int)j);
+        if (my_count) mbar_wait(full0, 0u);
+    }
+    if (g == NG - 1) bar_arrive(1 + NG, 2 * gthreads);     // the table starts out free for group 0
+    bar_sync(id_sync, gthreads);                           // first record visible to the group
 
-    const long long first = blockIdx.x;
-    const long long mine = first < P.n_tiles ? (P.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
-    const long long n_iter = (mine + ng - 1) / ng;
-    TileWalk walk;
-    walk.init(P, first + (long long)g * gridDim.x < P.n_tiles ? first + (long long)g * gridDim.x : 0,
-              (long long)ng * gridDim.x);
-    for (long long it = 0; it < n_iter; ++it, walk.next()) {
-        const int buf = (int)(it & 1);
-        const long long kk = (long long)ng * it + g;
-        const bool active = kk < mine;
-        const long long t = first + kk * gridDim.x;
-        Tile T;
-        T.h = 0; T.w = 0; T.n = 0;
+    int s = 0;
+    uint32_t phase = 0u;
+    for (uint32_t j = 0; j < n_iter; ++j, t += t_step) {
+        const bool active = j < my_count;
+        const unsigned char* rec = stage0 + (size_t)s * rec_bytes;
+        K3Group Gp;
+        Gp.q8 = reinterpret_cast<uint32_t*>(const_cast<unsigned char*>(rec) + sizeof(K3RecHdr));
+        Gp.mbits = Gp.q8 + q8w;
+        int bx[4] = {0, -1, 0, -1}, tw = 0;
         if (active) {
-            T = resolve_tile_rs(P, walk.row, walk.slot);
-            const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
-            const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
-            const int nfull = T.n >> 3, rem = T.n & 7;
-            uint8_t* mbytes = reinterpret_cast<uint8_t*>(Gp.mbits);
-
-            // ---- 1. tile maximum (over the mask when masked); stage the mask bits and their bounding box ----
-            uint32_t mx2 = 0u;
-            int brmin = 1 << 30, brmax = -1, bcmin = 1 << 30, bcmax = -1;
-            double vmaxd = 0.0;
-            if (k1_max) vmaxd = T.out_row[P.col_basic + kNBasic * T.slot + 10];
-            for (int idx = gt; idx < nfull && (MASKED || !k1_max); idx += gthreads) {
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (!k1_max) v = ld_reuse(px4 + idx);
-                if (MASKED) {
-                    const uint2 m = __ldg(mk2 + idx);
-                    const uint32_t c0 = __vcmpne4(m.x, 0u), c1 = __vcmpne4(m.y, 0u);
-                    // 8 mask bytes -> 8 bits (byte k -> bit k)
-                    const uint32_t b0 = ((c0 & 0x01010101u) * 0x01020408u) >> 24;
-                    const uint32_t b1 = ((c1 & 0x01010101u) * 0x01020408u) >> 24;
-                    const uint32_t bits8 = (b0 & 0xfu) | ((b1 & 0xfu) << 4);
-                    mbytes[idx] = (uint8_t)bits8;
-                    if (bits8) {
-                        const int p0 = 8 * idx, ra = p0 / T.w, ca = p0 - ra * T.w;
-                        if (ca + 7 < T.w) {                // the 8 pixels lie in one row
-                            brmin = min(brmin, ra); brmax = max(brmax, ra);
-                            bcmin = min(bcmin, ca + __ffs(bits8) - 1); bcmax = max(bcmax, ca + 31 - __clz(bits8));
-                        } else {                           // straddles rows: be conservative
-                            brmin = min(brmin, ra); brmax = max(brmax, (p0 + 7) / T.w);
-                            bcmin = 0; bcmax = T.w - 1;
-                        }
-                    }
-                    v.x &= __byte_perm(c0, 0u, 0x1100); v.y &= __byte_perm(c0, 0u, 0x3322);
-                    v.z &= __byte_perm(c1, 0u, 0x1100); v.w &= __byte_perm(c1, 0u, 0x3322);
-                }
-                mx2 = __vmaxu2(mx2, __vmaxu2(__vmaxu2(v.x, v.y), __vmaxu2(v.z, v.w)));
-            }
-            if (gt == 0 && rem) {                          // tail pixels (< 8): one thread, in order
-                uint32_t bits = 0u;
-                for (int k = 0; k < rem; ++k) {
-                    const int i = nfull * 8 + k;
-                    const bool ok = !MASKED || T.mk[i] != 0;
-                    if (ok) {
-                        bits |= 1u << k;
-                        if (!k1_max) mx2 = __vmaxu2(mx2, (uint32_t)T.px[i]);
-                        const int ra = i / T.w, ca = i - ra * T.w;
-                        brmin = min(brmin, ra); brmax = max(brmax, ra); bcmin = min(bcmin, ca); bcmax = max(bcmax, ca);
-                    }
-                }
-                if (MASKED) mbytes[nfull] = (uint8_t)bits;
-            }
-            if (MASKED) {
-                brmin = __reduce_min_sync(0xffffffffu, brmin); brmax = __reduce_max_sync(0xffffffffu, brmax);
-                bcmin = __reduce_min_sync(0xffffffffu, bcmin); bcmax = __reduce_max_sync(0xffffffffu, bcmax);
-                if (lane == 0 && brmax >= 0) {
-                    atomicMin(&H.box[buf][0], brmin); atomicMax(&H.box[buf][1], brmax);
-                    atomicMin(&H.box[buf][2], bcmin); atomicMax(&H.box[buf][3], bcmax);
-                }
-            }
-            uint32_t vmax;
-            if (k1_max) {
-                vmax = (vmaxd == vmaxd) ? (uint32_t)vmaxd : 0u;      // NaN: empty mask, no pair exists anyway
-            } else {
-                const uint32_t wm = __reduce_max_sync(0xffffffffu, max(mx2 & 0xffffu, mx2 >> 16));
-                if (lane == 0) H.wmax[gw] = wm;
-                ring_group_sync(R);
-                vmax = lane < R.gwarps ? H.wmax[lane] : 0u;
-                vmax = __reduce_max_sync(0xffffffffu, vmax);
-            }
-
-            // ---- 2. quantise to 8 bits into shared memory ----
-            uint32_t mul = 0, sh = 24;
-            if (lane == 0) k3_magic(vmax, mul, sh);
-            mul = __shfl_sync(0xffffffffu, mul, 0);
-            sh = __shfl_sync(0xffffffffu, sh, 0);
-            for (int idx = gt; idx < nfull; idx += gthreads) {
-                const uint4 v = ld_reuse(px4 + idx);
-                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-                uint32_t q[2] = {0u, 0u};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // pixels outside the mask may exceed vmax; they never enter a pair, clamp them
-                    uint32_t a = k3_quant(w4[k] & 0xffffu, mul, sh), b = k3_quant(w4[k] >> 16, mul, sh);
-                    if (MASKED) { a = min(a, 255u); b = min(b, 255u); }
-                    q[k >> 1] |= (a | (b << 8)) << (16 * (k & 1));
-                }
-                *reinterpret_cast<uint2*>(Gp.q8 + 2 * idx) = make_uint2(q[0], q[1]);
-            }
-            if (gt < rem) {
-                const int i = nfull * 8 + gt;
-                reinterpret_cast<uint8_t*>(Gp.q8)[i] = (uint8_t)min(k3_quant(T.px[i], mul, sh), 255u);
-            }
+            const K3RecHdr& Hd = *reinterpret_cast<const K3RecHdr*>(rec);
+            bx[0] = Hd.box[0]; bx[1] = Hd.box[1]; bx[2] = Hd.box[2]; bx[3] = Hd.box[3];
+            tw = Hd.w;
         }
-        ring_group_sync(R);                                // this tile staged; the previous one is complete
-        deferred_epilogue(buf ^ 1);
 
-        // ---- 3. one GLCM per direction ----
-        // box of pixels that can take part in a pair: the tile, or the mask's bounding box
-        int bx[4] = {0, T.h - 1, 0, T.w - 1};
-        if (MASKED && active) { bx[0] = H.box[buf][0]; bx[1] = H.box[buf][1]; bx[2] = H.box[buf][2]; bx[3] = H.box[buf][3]; }
-        for (int a = 0; a < P.n_angles; ++a) {
-            const K3Geom G = k3_geom(T.w, P.dr[a], P.dc[a], bx[0], bx[1], bx[2], bx[3]);
-            uint32_t I4[kK3Cache], J4[kK3Cache], vm[kK3Cache];
-            if (active) {
-                // table-free: pair-stream sums; the first kK3Cache items of a thread stay in registers
-                K3Acc A = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0};
 #pragma unroll
-                for (int i = 0; i < kK3Cache; ++i) {
-                    const int item = gt + i * gthreads;
-                    vm[i] = 0u; I4[i] = 0u; J4[i] = 0u;
-                    if (item < G.items && k3_item<MASKED>(Gp, G, item, I4[i], J4[i], vm[i]))
-                        k3_sums<MASKED>(S, I4[i], J4[i], vm[i], A);
-                }
-                for (int item = gt + kK3Cache * gthreads; item < G.items; item += gthreads) {
-                    uint32_t i4, j4, v;
-                    if (k3_item<MASKED>(Gp, G, item, i4, j4, v)) k3_sums<MASKED>(S, i4, j4, v, A);
-                }
-                uint32_t red[6] = {A.si, A.sj, A.sii, A.sjj, A.sij, A.sd};
+        for (int a = 0; a < kMaxAngles; ++a) {
+            if (a >= P.n_angles) break;
+            // ---- off the table: this direction's first items become hits in registers ----
+            const K3Geom G = k3_geom(tw, P.dr[a], P.dc[a], bx[0], bx[1], bx[2], bx[3]);
+            uint32_t hit[kCache][4];
+            uint32_t valid = 0u, sold = 0u, mm = 0u, nd = 0u;
 #pragma unroll
-                for (int k = 0; k < 6; ++k) red[k] = __reduce_add_sync(0xffffffffu, red[k]);
-                const uint32_t mm = __reduce_add_sync(0xffffffffu, A.m);
-                // per-thread double -> 2^-40 fixed point, then exact integer sums (order independent)
-                const unsigned long long hf = warp_sum_redux((unsigned long long)__double2ll_rn(A.hom * 1099511627776.0));
-                if (lane == 0) {
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) atomicAdd(&H.acc[buf][a][k], red[k]);
-                    atomicAdd(&H.acc[buf][a][7], mm);
-                    H.whom[buf][a][gw] = hf;
+            for (int i = 0; i < kCache; ++i) {
+                const int item = gt + i * gthreads;
+                uint32_t I4, J4, vm;
+                if (item < G.items && k3_item<MASKED>(Gp, G, item, I4, J4, vm)) {
+                    k3_hits<MASKED>(I4, J4, vm, dummy_off, hit[i]);
+                    valid |= 1u << i;
+                    mm += __popc(vm) >> 3;
+                    nd += 4u - (__popc(vm) >> 3);
                 }
             }
-            ring_acquire(R);                               // ---- table owned by this group ----
-            if (active) {
-                uint32_t sold = 0u;
+            bar_sync(id_mine, 2 * gthreads);               // ---- table owned by this group ----
 #pragma unroll
-                for (int i = 0; i < kK3Cache; ++i)
-                    if (vm[i]) k3_bins<0, MASKED>(S, I4[i], J4[i], vm[i], sold);
-                for (int item = gt + kK3Cache * gthreads; item < G.items; item += gthreads) {
-                    uint32_t i4, j4, v;
-                    if (k3_item<MASKED>(Gp, G, item, i4, j4, v)) k3_bins<0, MASKED>(S, i4, j4, v, sold);
+            for (int i = 0; i < kCache; ++i)
+                if (valid & (1u << i)) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) k3_hit(hist_addr, hit[i][k], sold);
                 }
-                ring_group_sync(R);                        // bins complete
-                if (DUMP) {
-                    uint32_t* dst = P.counts + (t * P.n_angles + a) * 65536ll;
+            for (int item = gt + kCache * gthreads; item < G.items; item += gthreads) {
+                uint32_t I4, J4, vm, h4[4];
+                if (k3_item<MASKED>(Gp, G, item, I4, J4, vm)) {
+                    k3_hits<MASKED>(I4, J4, vm, dummy_off, h4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) k3_hit(hist_addr, h4[k], sold);
+                    mm += __popc(vm) >> 3;
+                    nd += 4u - (__popc(vm) >> 3);
+                }
+            }
+            bar_sync(id_sync, gthreads);                   // bins of this direction complete
+            if (DUMP) {
+                if (active) {
+                    uint32_t* dst = P.counts + ((long long)t * P.n_angles + a) * 65536ll;
                     for (int k = gt; k < 32768; k += gthreads) {
                         const uint32_t wv = S.hist[k];
                         reinterpret_cast<uint2*>(dst)[k] = make_uint2(wv & 0xffffu, wv >> 16);
                     }
-                    ring_group_sync(R);
                 }
-                uint32_t dummy = 0u;
-#pragma unroll
-                for (int i = 0; i < kK3Cache; ++i)
-                    if (vm[i]) k3_bins<2, MASKED>(S, I4[i], J4[i], vm[i], dummy);
-                for (int item = gt + kK3Cache * gthreads; item < G.items; item += gthreads) {
-                    uint32_t i4, j4, v;
-                    if (k3_item<MASKED>(Gp, G, item, i4, j4, v)) k3_bins<2, MASKED>(S, i4, j4, v, dummy);
-                }
-                ring_release(R);                           // ---- hand the table to the next group ----
-                sold = __reduce_add_sync(0xffffffffu, sold);
-                if (lane == 0) atomicAdd(&H.acc[buf][a][6], sold);
-            } else {
-                ring_release(R);
+                bar_sync(id_sync, gthreads);
             }
+#pragma unroll
+            for (int i = 0; i < kCache; ++i)
+                if (valid & (1u << i)) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) k3_unhit(hist_addr, hit[i][k]);
+                }
+            for (int item = gt + kCache * gthreads; item < G.items; item += gthreads) {
+                uint32_t I4, J4, vm, h4[4];
+                if (k3_item<MASKED>(Gp, G, item, I4, J4, vm)) {
+                    k3_hits<MASKED>(I4, J4, vm, dummy_off, h4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) k3_unhit(hist_addr, h4[k]);
+                }
+            }
+            // ---- hand the clean table on (the very last hand-over has no taker) ----
+            if (!(g == NG - 1 && j + 1 == n_iter && a + 1 == P.n_angles)) bar_arrive(id_next, 2 * gthreads);
+            sold -= nd * (nd - 1u) / 2u;                   // the dummy word returned 0 .. nd-1
+            const uint32_t so = __reduce_add_sync(0xffffffffu, sold);
+            const uint32_t mo = __reduce_add_sync(0xffffffffu, mm);
+            if (lane == 0 && mo) { atomicAdd(&S.acc[g][a][0], so); atomicAdd(&S.acc[g][a][1], mo); }
         }
-
-        // ---- 4. the epilogue is deferred to the next round (after its staging barrier) ----
-        prev_active = active;
-        if (active) {
-            prev_row = T.out_row; prev_status = T.status; prev_slot = T.slot; prev_h = T.h; prev_w = T.w;
+        // next record (copy started ns rounds ago) must have landed before the group moves on
+        const int s_next = s + 1 == ns ? 0 : s + 1;
+        const uint32_t phase_next = s + 1 == ns ? phase ^ 1u : phase;
+        if (gt == 0 && j + 1 < my_count) mbar_wait(full0 + 8 * s_next, phase_next);
+        bar_sync(id_sync, gthreads);                       // sums final, this record no longer read, next one visible
+        if (active && gw < P.n_angles && lane == 0) {
+            double* out_row = P.out + (long long)(t / (uint32_t)P.c_out) * P.row_stride;
+            k3_epilogue(P, out_row, (int)(t % (uint32_t)P.c_out), gw, (unsigned long long)S.acc[g][gw][0],
+                        (long long)S.acc[g][gw][1]);
+            S.acc[g][gw][0] = 0u;
+            S.acc[g][gw][1] = 0u;
         }
+        if (gt == 0 && j + ns < my_count) fetch(t + (uint32_t)ns * t_step, s);
+        s = s_next;
+        phase = phase_next;
     }
-    ring_group_sync(R);                                    // last tile of this group complete
-    deferred_epilogue((int)(n_iter & 1) ^ 1);
 }
 
 }  // namespace imfeat
