@@ -36,7 +36,7 @@ struct K3RecHdr {
     int box[4];                      // rows [box0, box1], columns [box2, box3] that can hold pairs
     int h, w, pad[2];
 };
-__host__ __device__ inline int k3_q8_words(int max_pixels) { return (max_pixels / 4 + 4 + 3) & ~3; }
+__host__ __device__ inline int k3_q8_words(int max_pixels) { return (max_pixels / 4 + 8 + 3) & ~3; }
 __host__ __device__ inline int k3_mb_words(int max_pixels, bool masked) { return masked ? ((max_pixels / 32 + 2 + 3) & ~3) : 0; }
 __host__ __device__ inline size_t k3_rec_bytes(int max_pixels, bool masked) {
     return sizeof(K3RecHdr) + 4 * (size_t)(k3_q8_words(max_pixels) + k3_mb_words(max_pixels, masked));
@@ -44,7 +44,6 @@ __host__ __device__ inline size_t k3_rec_bytes(int max_pixels, bool masked) {
 
 struct K3Smem {
     uint32_t hist[32768];
-    uint32_t dummy[kK3Threads];                 // at hist + 0x20000: one word per thread for its non-existent pairs
     unsigned long long full[4][kK3MaxStages];   // mbarriers: record landed
     uint32_t acc[4][kMaxAngles][2];             // per group and direction: sum of returned old counts, pair count
 };
@@ -87,20 +86,21 @@ __device__ __forceinline__ uint32_t k3_quant(uint32_t x, uint32_t mul, uint32_t 
     return (uint32_t)(((unsigned long long)(x * 255u) * mul) >> sh);
 }
 
-// four consecutive bytes starting at byte offset off (any alignment)
-__device__ __forceinline__ uint32_t k3_load4(const uint32_t* b, int off) {
-    const int w = off >> 2;
-    return __funnelshift_r(b[w], b[w + 1], (off & 3) << 3);
+// four mask bits expanded to 0xff / 0x00 bytes
+__device__ __forceinline__ uint32_t k3_expand4(uint32_t bits) {
+    return (((bits & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;
 }
-// four consecutive mask bits starting at bit offset off, expanded to 0xff / 0x00 bytes
-__device__ __forceinline__ uint32_t k3_mask4(const uint32_t* b, int off) {
+// 16 consecutive mask bits starting at bit offset off
+__device__ __forceinline__ uint32_t k3_bits16(const uint32_t* b, int off) {
     const int w = off >> 5;
-    const uint32_t bits = __funnelshift_r(b[w], b[w + 1], off & 31) & 0xfu;
-    return ((bits * 0x00204081u) & 0x01010101u) * 0xffu;
+    return __funnelshift_r(b[w], b[w + 1], off & 31) & 0xffffu;
 }
 
+// An item is a run of up to 16 horizontally consecutive pairs (4 groups of 4) of one row: the words
+// of both pixel runs are loaded once and funnel-shifted into place.
 struct K3Geom {
-    int nrows, r0, c0, c1, gpr, lg, items, w, doff;
+    int nrows, r0, c0, c1, ipr, items, w, doff;
+    uint32_t rcp;                                  // floor(2^32 / ipr) + 1: row = umulhi(item, rcp)
 };
 // Pairs (r, c) -> (r + dr, c + dc) with both pixels inside the box rows [br0, br1], columns
 // [bc0, bc1] (the whole tile, or the bounding box of the mask: pairs outside it cannot exist).
@@ -112,49 +112,59 @@ __device__ __forceinline__ K3Geom k3_geom(int w, int dr, int dc, int br0, int br
     G.c1 = bc1 + 1 - (dc > 0 ? dc : 0);
     G.w = w;
     G.doff = dr * w + dc;
-    if (G.nrows <= 0 || G.c1 <= G.c0) { G.items = 0; G.gpr = 0; G.lg = 0; G.nrows = 0; return G; }
-    G.gpr = (G.c1 - G.c0 + 3) >> 2;                // groups of 4 pairs per row
-    G.lg = G.gpr <= 1 ? 0 : 32 - __clz(G.gpr - 1); // ceil(log2 gpr): row index = item >> lg
-    G.items = G.nrows << G.lg;
+    if (G.nrows <= 0 || G.c1 <= G.c0) { G.items = 0; G.ipr = 1; G.rcp = 0u; G.nrows = 0; return G; }
+    G.ipr = (G.c1 - G.c0 + 15) >> 4;               // items per row
+    G.rcp = G.ipr > 1 ? 0xffffffffu / (uint32_t)G.ipr + 1u : 0u;
+    G.items = G.nrows * G.ipr;
     return G;
 }
 
-// Load one item (4 horizontally consecutive pairs): quantised bytes of both pixels and the
-// byte mask of the pairs that exist (inside the image, and inside the mask when MASKED).
+// Load one item: the quantised bytes of both pixels of its 16 pairs (I4[k], J4[k]: pairs 4k..4k+3;
+// bytes of pairs that do not exist are whatever lies there) and one bit per pair that exists (inside
+// the image, and inside the mask when MASKED).  False if none does.
 template <bool MASKED>
-__device__ __forceinline__ bool k3_item(const K3Group& Gp, const K3Geom& G, int item, uint32_t& I4,
-                                        uint32_t& J4, uint32_t& vm) {
-    const int r = G.r0 + (item >> G.lg), cg = item & ((1 << G.lg) - 1);
-    if (cg >= G.gpr) { vm = 0u; I4 = J4 = 0u; return false; }
-    const int c = G.c0 + 4 * cg;
-    const int valid = min(4, G.c1 - c);
-    const int oi = r * G.w + c, oj = oi + G.doff;
-    vm = valid == 4 ? 0xffffffffu : ((1u << (8 * valid)) - 1u);
-    if (MASKED) vm &= k3_mask4(Gp.mbits, oi) & k3_mask4(Gp.mbits, oj);
-    I4 = k3_load4(Gp.q8, oi) & vm;
-    J4 = k3_load4(Gp.q8, oj) & vm;
-    return vm != 0u;
+__device__ __forceinline__ bool k3_item16(const K3Group& Gp, const K3Geom& G, int item, uint32_t (&I4)[4],
+                                          uint32_t (&J4)[4], uint32_t& pm) {
+    const int r = G.ipr > 1 ? (int)__umulhi((uint32_t)item, G.rcp) : item;
+    const int c = G.c0 + 16 * (item - r * G.ipr);
+    const int nv = min(16, G.c1 - c);
+    const int oi = (G.r0 + r) * G.w + c, oj = oi + G.doff;
+    pm = 0xffffu >> (16 - nv);
+    if (MASKED) {
+        pm &= k3_bits16(Gp.mbits, oi) & k3_bits16(Gp.mbits, oj);
+        if (pm == 0u) return false;
+    }
+    const uint32_t* bi = Gp.q8 + (oi >> 2);
+    const uint32_t* bj = Gp.q8 + (oj >> 2);
+    const uint32_t si = (uint32_t)(oi & 3) << 3, sj = (uint32_t)(oj & 3) << 3;
+    uint32_t wi[5], wj[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { wi[k] = bi[k]; wj[k] = bj[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        I4[k] = __funnelshift_r(wi[k], wi[k + 1], si);
+        J4[k] = __funnelshift_r(wj[k], wj[k + 1], sj);
+    }
+    return true;
 }
 
-// Pair-stream sums of one item.  Unmasked tiles run branch-free: the bytes of non-existent pairs
-// (row tails) are zero, so they add nothing to the integer sums and exactly homtab[0] = 1.0 to the
-// homogeneity sum, which the epilogue subtracts again.
-template <bool MASKED>
+// Pair-stream sums of one group of 4 pairs; vm = 0xff per pair that exists.  Bytes of pairs that do not
+// exist are zeroed, so they add nothing to the integer sums and exactly homtab[0] = 1.0 each to the
+// homogeneity sum, which the epilogue subtracts again (16 per item minus the pair count).
 __device__ __forceinline__ void k3_sums(const double* homtab, uint32_t I4, uint32_t J4, uint32_t vm, K3Acc& A) {
+    I4 &= vm;
+    J4 &= vm;
     A.si = __dp4a(I4, 0x01010101u, A.si);
     A.sj = __dp4a(J4, 0x01010101u, A.sj);
     A.sii = __dp4a(I4, I4, A.sii);
     A.sjj = __dp4a(J4, J4, A.sjj);
     A.sij = __dp4a(I4, J4, A.sij);
     A.sd += __vsadu4(I4, J4);
-    A.m += __popc(vm) >> 3;
     const uint32_t D4 = __vabsdiffu4(I4, J4);
     A.hom += homtab[D4 & 0xffu];
     A.hom += homtab[(D4 >> 8) & 0xffu];
     A.hom += homtab[(D4 >> 16) & 0xffu];
     A.hom += homtab[D4 >> 24];
-    // masked tiles: take the 1.0 of every missing pair out again right away (exact)
-    if (MASKED) A.hom -= (double)(4 - (__popc(vm) >> 3));
 }
 
 // ---- the bins ------------------------------------------------------------------------------------
@@ -163,22 +173,27 @@ __device__ __forceinline__ void k3_sums(const double* homtab, uint32_t I4, uint3
 // bank would otherwise depend on j alone (measured: 7.2 wavefronts per ATOMS without the swizzle).
 // While the group does not own the table, every pair becomes a "hit" in a register:
 //     hit = word << 16 | 1 << 8 * (j & 1)
-// and a pair that does not exist (row tail, outside the mask) the thread's own dummy word with an
-// increment of zero, so the table phase is branch-free and four instructions per pair:
+// (a pair that does not exist -- row tail, outside the mask -- gets an increment of zero on whatever
+// word the bytes lying there give), so the table phase is branch-free and four instructions per pair:
 //     addr = hit >> 14;  inc = PRMT(hit) = 1 << 16 * (j & 1);  old = ATOMS.ADD [addr], inc;
 //     sold = IDP.2A(old, hit) + sold       (= old count of that bin)
 // sum_bins c^2 = 2 * sum(old) + M  (c^2 = sum_{k<c} (2k+1)), so the bins are never read back; clearing
 // re-walks the hits.  (Merging equal hits of a warp with match.any first was measured 4x slower.)
-template <bool MASKED>
-__device__ __forceinline__ void k3_hits(uint32_t I4, uint32_t J4, uint32_t vm, uint32_t dummy_hit, uint32_t (&h)[4]) {
-    const uint32_t K01 = __byte_perm(J4, I4, 0x5140);   // [j0, i0, j1, i1]: keys i << 8 | j
-    const uint32_t K23 = __byte_perm(J4, I4, 0x7362);   // [j2, i2, j3, i3]
-    const uint32_t key[4] = {K01 & 0xffffu, K01 >> 16, K23 & 0xffffu, K23 >> 16};
+
+// two hits from two 16-bit keys i << 8 | j in K; M = 0xffff per key whose pair exists
+__device__ __forceinline__ void k3_hits2(uint32_t K, uint32_t M, uint32_t& ha, uint32_t& hb) {
+    const uint32_t W = ((K >> 1) & 0x7fff7fffu) ^ ((K >> 6) & 0x007c007cu);       // swizzled words
+    const uint32_t S = ((K & 0x00010001u) * 0xffu + 0x00010001u) & M;             // 1 << 8 * (j & 1), or 0
+    ha = __byte_perm(S, W, 0x5410);
+    hb = __byte_perm(S, W, 0x7632);
+}
+// the 16 hits of an item; pairs that do not exist keep whatever word their bytes give, with increment 0
+__device__ __forceinline__ void k3_hits16(const uint32_t (&I4)[4], const uint32_t (&J4)[4], uint32_t pm, uint32_t (&h)[16]) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const uint32_t word = (key[k] >> 1) ^ ((key[k] >> 6) & 0x7cu);
-        const uint32_t hit = (word << 16) | (1u << ((key[k] & 1u) << 3));
-        h[k] = (vm & (0xffu << (8 * k))) ? hit : dummy_hit;
+        const uint32_t vm = k3_expand4(pm >> (4 * k));
+        k3_hits2(__byte_perm(J4[k], I4[k], 0x5140), __byte_perm(vm, 0u, 0x1100), h[4 * k], h[4 * k + 1]);
+        k3_hits2(__byte_perm(J4[k], I4[k], 0x7362), __byte_perm(vm, 0u, 0x3322), h[4 * k + 2], h[4 * k + 3]);
     }
 }
 // increments the bin of a hit and accumulates its old count
@@ -210,7 +225,7 @@ k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict
     extern __shared__ __align__(16) unsigned char k3_smem_raw[];
     K3Smem& S = *reinterpret_cast<K3Smem*>(k3_smem_raw);
     constexpr int gthreads = kK3Threads / NG;
-    constexpr int kCache = 1024 / gthreads;                // items (4 pairs each) per thread held in registers
+    constexpr int kCache = 256 / gthreads + (gthreads > 256 ? 1 : 0);   // items (16 pairs each) per thread held in registers
     const int tid = threadIdx.x, lane = tid & 31;
     const int g = tid / gthreads, gt = tid % gthreads, gw = gt >> 5;
     const uint32_t rec_bytes = (uint32_t)k3_rec_bytes(max_pixels, MASKED);
@@ -218,11 +233,9 @@ k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict
     unsigned char* stage0 = k3_smem_raw + sizeof(K3Smem) + (size_t)g * ns * rec_bytes;
     const uint32_t full0 = smem_addr(&S.full[g][0]);
     const uint32_t hist_addr = smem_addr(S.hist);
-    const uint32_t dummy_hit = (0x8000u + (uint32_t)tid) << 16;      // this thread's dummy word, m = 0
     const int id_sync = 1 + g, id_mine = 1 + NG + g, id_next = 1 + NG + (g + 1) % NG;
 
     for (int k = tid; k < 32768; k += kK3Threads) S.hist[k] = 0u;
-    S.dummy[tid] = 0u;
     if (tid < 4 * kMaxAngles * 2) (&S.acc[0][0][0])[tid] = 0u;
     if (tid == 0) {
         for (int i = 0; i < 4 * kK3MaxStages; ++i) mbar_init(smem_addr(&S.full[0][0]) + 8 * i, 1);
@@ -268,15 +281,15 @@ k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict
             if (a >= P.n_angles) break;
             // ---- off the table: this direction's first items become hits in registers ----
             const K3Geom G = k3_geom(tw, P.dr[a], P.dc[a], bx[0], bx[1], bx[2], bx[3]);
-            uint32_t hit[kCache][4];
+            uint32_t hit[kCache][16];
             uint32_t sold = 0u, mm = 0u, valid = 0u;
 #pragma unroll
             for (int i = 0; i < kCache; ++i) {
                 const int item = gt + i * gthreads;
-                uint32_t I4, J4, vm;
-                if (item < G.items && k3_item<MASKED>(Gp, G, item, I4, J4, vm)) {
-                    k3_hits<MASKED>(I4, J4, vm, dummy_hit, hit[i]);
-                    mm += __popc(vm) >> 3;
+                uint32_t I4[4], J4[4], pm;
+                if (item < G.items && k3_item16<MASKED>(Gp, G, item, I4, J4, pm)) {
+                    k3_hits16(I4, J4, pm, hit[i]);
+                    mm += __popc(pm);
                     valid |= 1u << i;
                 }
             }
@@ -285,15 +298,15 @@ k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict
             for (int i = 0; i < kCache; ++i)
                 if (valid & (1u << i)) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) k3_hit(hist_addr, hit[i][k], sold);
+                    for (int k = 0; k < 16; ++k) k3_hit(hist_addr, hit[i][k], sold);
                 }
             for (int item = gt + kCache * gthreads; item < G.items; item += gthreads) {
-                uint32_t I4, J4, vm, h4[4];
-                if (k3_item<MASKED>(Gp, G, item, I4, J4, vm)) {
-                    k3_hits<MASKED>(I4, J4, vm, dummy_hit, h4);
+                uint32_t I4[4], J4[4], pm, h16[16];
+                if (k3_item16<MASKED>(Gp, G, item, I4, J4, pm)) {
+                    k3_hits16(I4, J4, pm, h16);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) k3_hit(hist_addr, h4[k], sold);
-                    mm += __popc(vm) >> 3;
+                    for (int k = 0; k < 16; ++k) k3_hit(hist_addr, h16[k], sold);
+                    mm += __popc(pm);
                 }
             }
             bar_sync(id_sync, gthreads);                   // bins of this direction complete
@@ -312,14 +325,14 @@ k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict
             for (int i = 0; i < kCache; ++i)
                 if (valid & (1u << i)) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) k3_unhit(hist_addr, hit[i][k]);
+                    for (int k = 0; k < 16; ++k) k3_unhit(hist_addr, hit[i][k]);
                 }
             for (int item = gt + kCache * gthreads; item < G.items; item += gthreads) {
-                uint32_t I4, J4, vm, h4[4];
-                if (k3_item<MASKED>(Gp, G, item, I4, J4, vm)) {
-                    k3_hits<MASKED>(I4, J4, vm, dummy_hit, h4);
+                uint32_t I4[4], J4[4], pm, h16[16];
+                if (k3_item16<MASKED>(Gp, G, item, I4, J4, pm)) {
+                    k3_hits16(I4, J4, pm, h16);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) k3_unhit(hist_addr, h4[k]);
+                    for (int k = 0; k < 16; ++k) k3_unhit(hist_addr, h16[k]);
                 }
             }
             // ---- hand the clean table on (the very last hand-over has no taker) ----

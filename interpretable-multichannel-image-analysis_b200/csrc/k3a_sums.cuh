@@ -134,18 +134,18 @@ k3a_glcm_sums_kernel(const __grid_constant__ Params P, unsigned char* __restrict
         // ---- 3. one lane-strided pass over the pair groups per direction ----
         for (int a = 0; a < P.n_angles; ++a) {
             const K3Geom G = k3_geom(T.w, P.dr[a], P.dc[a], bx[0], bx[1], bx[2], bx[3]);
-            K3Acc A0 = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0}, A1 = A0;
-            int item = lane;
-            for (; item + 32 < G.items; item += 64) {      // two independent chains
-                uint32_t i0, j0, v0, i1, j1, v1;
-                const bool e0 = k3_item<MASKED>(Gp, G, item, i0, j0, v0);
-                const bool e1 = k3_item<MASKED>(Gp, G, item + 32, i1, j1, v1);
-                if (e0) k3_sums<MASKED>(homtab, i0, j0, v0, A0);
-                if (e1) k3_sums<MASKED>(homtab, i1, j1, v1, A1);
-            }
-            if (item < G.items) {
-                uint32_t i0, j0, v0;
-                if (k3_item<MASKED>(Gp, G, item, i0, j0, v0)) k3_sums<MASKED>(homtab, i0, j0, v0, A0);
+            K3Acc A0 = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0}, A1 = A0;   // two independent chains
+            uint32_t nproc = 0u;                           // items this lane went through
+            for (int item = lane; item < G.items; item += 32) {
+                uint32_t I4[4], J4[4], pm;
+                if (k3_item16<MASKED>(Gp, G, item, I4, J4, pm)) {
+                    k3_sums(homtab, I4[0], J4[0], k3_expand4(pm), A0);
+                    k3_sums(homtab, I4[1], J4[1], k3_expand4(pm >> 4), A1);
+                    k3_sums(homtab, I4[2], J4[2], k3_expand4(pm >> 8), A0);
+                    k3_sums(homtab, I4[3], J4[3], k3_expand4(pm >> 12), A1);
+                    A0.m += __popc(pm);
+                    ++nproc;
+                }
             }
             const uint32_t si = __reduce_add_sync(0xffffffffu, A0.si + A1.si);
             const uint32_t sj = __reduce_add_sync(0xffffffffu, A0.sj + A1.sj);
@@ -154,6 +154,7 @@ k3a_glcm_sums_kernel(const __grid_constant__ Params P, unsigned char* __restrict
             const uint32_t sij = __reduce_add_sync(0xffffffffu, A0.sij + A1.sij);
             const uint32_t sd = __reduce_add_sync(0xffffffffu, A0.sd + A1.sd);
             const uint32_t mm = __reduce_add_sync(0xffffffffu, A0.m + A1.m);
+            const uint32_t np = __reduce_add_sync(0xffffffffu, nproc);
             // per-lane double sums (fixed lane-strided order) are rounded to 2^-40 fixed point, so the
             // warp reduction is an integer sum and the result does not depend on which warp ran the tile
             const unsigned long long homfix =
@@ -165,8 +166,8 @@ k3a_glcm_sums_kernel(const __grid_constant__ Params P, unsigned char* __restrict
                     o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[5] = 1.0;
                     if (T.status) atomicOr(T.status, kStNoPairs);
                 } else {
-                    // unmasked: the non-existent pairs of the branch-free path added exactly 1.0 each
-                    const long long D = MASKED ? 0ll : 4ll * G.nrows * G.gpr - M;
+                    // the pairs of the processed items that do not exist added exactly 1.0 each
+                    const long long D = 16ll * np - M;
                     const double Md = (double)M;
                     const long long Si = si, Sj = sj, Sii = sii, Sjj = sjj, Sij = sij;
                     o[0] = (double)(Sii + Sjj - 2 * Sij) / Md;
