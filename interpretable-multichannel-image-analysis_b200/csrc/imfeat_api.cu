@@ -12,7 +12,7 @@
 #include "k1_moments.cuh"
 #include "k2_order_entropy.cuh"
 #include "k3_glcm.cuh"
-#include "k3a_sums.cuh"
+#include "k3a_stage.cuh"
 #include "k4_shape.cuh"
 
 using namespace imfeat;
@@ -394,21 +394,21 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
     if (o->want_glcm) {
         const int g3 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
         const int maxpx = ((P.hs * P.ws + 7) & ~7);
-        // K3a: quantise; contrast, dissimilarity, homogeneity, correlation straight from the pair stream
-        // (warp per tile); leaves one record per tile for K3 in a stream-ordered scratch buffer
+        // K3a: maximum, quantisation, mask bits (warp per tile); leaves one record per tile for K3 in a
+        // stream-ordered scratch buffer
         const size_t smem_a = k3a_smem_bytes(maxpx, masked);
         if (ctx->k3a_maxpx != maxpx) {
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k3a_bps[0], k3a_glcm_sums_kernel<false>, kK3aThreads, k3a_smem_bytes(maxpx, false)));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k3a_bps[1], k3a_glcm_sums_kernel<true>, kK3aThreads, k3a_smem_bytes(maxpx, true)));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k3a_bps[0], k3a_glcm_stage_kernel<false>, kK3aThreads, k3a_smem_bytes(maxpx, false)));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k3a_bps[1], k3a_glcm_stage_kernel<true>, kK3aThreads, k3a_smem_bytes(maxpx, true)));
             ctx->k3a_maxpx = maxpx;
         }
         unsigned char* recs = nullptr;
         CU(cudaMallocFromPoolAsync((void**)&recs, k3_rec_bytes(maxpx, masked) * (size_t)P.n_tiles, ctx->pool, st));
         const long long resa = sm * (ctx->k3a_bps[masked] > 0 ? ctx->k3a_bps[masked] : 1);
         const int ga = (int)(P.n_tiles < resa ? P.n_tiles : resa);
-        if (masked) k3a_glcm_sums_kernel<true><<<ga, kK3aThreads, smem_a, st>>>(P, recs, maxpx);
-        else k3a_glcm_sums_kernel<false><<<ga, kK3aThreads, smem_a, st>>>(P, recs, maxpx);
-        // K3: the bins (ASM, energy) on the shared-memory table, two groups taking turns
+        if (masked) k3a_glcm_stage_kernel<true><<<ga, kK3aThreads, smem_a, st>>>(P, recs, maxpx);
+        else k3a_glcm_stage_kernel<false><<<ga, kK3aThreads, smem_a, st>>>(P, recs, maxpx);
+        // K3: pair-stream sums and the bins on the shared-memory table, groups taking turns
         const int ns3 = k3_stages(maxpx, masked);
         launch_k3<false>(masked, k3_groups(maxpx, masked), g3, k3_smem_bytes(maxpx, masked), st, P, recs, maxpx, ns3);
         CU(cudaFreeAsync(recs, st));
@@ -516,8 +516,8 @@ int imfeat_glcm_counts_device(imfeat_ctx* ctx, const uint16_t* d_planes, const u
     unsigned char* recs = nullptr;
     CU(cudaMallocFromPoolAsync((void**)&recs, k3_rec_bytes(maxpx, masked) * (size_t)P.n_tiles, ctx->pool, st));
     const int ga = (int)(P.n_tiles < 16ll * ctx->sm_count ? P.n_tiles : 16ll * ctx->sm_count);
-    if (masked) k3a_glcm_sums_kernel<true><<<ga, kK3aThreads, k3a_smem_bytes(maxpx, true), st>>>(P, recs, maxpx);
-    else k3a_glcm_sums_kernel<false><<<ga, kK3aThreads, k3a_smem_bytes(maxpx, false), st>>>(P, recs, maxpx);
+    if (masked) k3a_glcm_stage_kernel<true><<<ga, kK3aThreads, k3a_smem_bytes(maxpx, true), st>>>(P, recs, maxpx);
+    else k3a_glcm_stage_kernel<false><<<ga, kK3aThreads, k3a_smem_bytes(maxpx, false), st>>>(P, recs, maxpx);
     const int ns3 = k3_stages(maxpx, masked);
     launch_k3<true>(masked, k3_groups(maxpx, masked), g3, k3_smem_bytes(maxpx, masked), st, P, recs, maxpx, ns3);
     CU(cudaFreeAsync(recs, st));

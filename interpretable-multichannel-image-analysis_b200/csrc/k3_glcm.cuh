@@ -7,16 +7,16 @@
 //
 // * quantiser: floor(255*x/max) with an exact multiply-shift reciprocal (bit-identical to the
 //   notebook's float64 expression for every uint16 pair; tests/test_oracle_cpu.py).
-// * the work is split over two kernels.  K3a (k3a_sums.cuh, one warp per tile) quantises the tile,
-//   computes the four properties that are linear in the matrix straight from the pair stream and
-//   leaves a per-tile record (header, quantised bytes, mask bits) in a scratch buffer.  K3 (this
-//   file) only builds the bins, for ASM and energy.
+// * two kernels.  K3a (k3a_stage.cuh, one warp per tile) finds the maximum, quantises the tile and
+//   leaves a per-tile record (header, quantised bytes, mask bits) in a scratch buffer.  K3 (this file)
+//   consumes the records: pair-stream sums and the bins.
 // * the 256x256 bins live in shared memory as 16-bit counters (two per 32-bit word, 128 KB), built
 //   with shared-memory atomics on the pair stream, dumped on request (parity), and only ever
 //   cleared sparsely by re-walking the pairs.  One persistent CTA per SM; its two 512-thread groups
 //   work on two tiles at a time and take turns on the table, handing it over with named barriers
 //   (bar.arrive / bar.sync: the waiting group is parked in hardware and issues nothing).  While one
-//   group owns the table the other loads the pair items of its next direction into registers.
+//   group owns the table the others load the pair items of their next direction, add up the pair-stream
+//   sums (contrast, dissimilarity, homogeneity, correlation need no bins) and turn the pairs into hits.
 // * records arrive through a shared-memory ring filled by cp.async.bulk (1-D TMA) completing on
 //   mbarriers, several tiles ahead, so staging costs no instructions.
 // * ASM = sum_bins c^2 is accumulated from the atomics' return values
@@ -42,10 +42,18 @@ __host__ __device__ inline size_t k3_rec_bytes(int max_pixels, bool masked) {
     return sizeof(K3RecHdr) + 4 * (size_t)(k3_q8_words(max_pixels) + k3_mb_words(max_pixels, masked));
 }
 
+// per group and direction, summed over the warps of the group
+struct K3AccS {
+    uint32_t s[8];                   // si sj sii sjj sij sd sold m
+    unsigned long long hom;          // sum of 1 / (1 + d^2) in 2^-40 fixed point
+    uint32_t np, pad;                // pairs walked (16 per item), existing or not
+};
 struct K3Smem {
     uint32_t hist[32768];
     unsigned long long full[4][kK3MaxStages];   // mbarriers: record landed
-    uint32_t acc[4][kMaxAngles][2];             // per group and direction: sum of returned old counts, pair count
+    double homtab[256];                         // 1 / (1 + d^2)
+    K3AccS acc[4][2][kMaxAngles];               // per group, tile parity (the epilogue of a tile overlaps the
+                                                // next tile's first sums) and direction
 };
 struct K3Group {                               // where the quantised tile and its mask bits live
     uint32_t* q8;                              // quantised pixels (bytes) + slack for unaligned reads
@@ -207,16 +215,28 @@ __device__ __forceinline__ void k3_unhit(uint32_t hist_addr, uint32_t h) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(hist_addr + (h >> 14)), "r"(0u) : "memory");
 }
 
-// ASM and energy of one direction from sum(old) and the pair count (the other four properties are
-// written by k3a_glcm_sums_kernel).
-__device__ __forceinline__ void k3_epilogue(const Params& P, double* out_row, int slot, int a,
-                                            unsigned long long sold, long long M) {
+// One direction's six properties from the exact integer sums.
+__device__ __forceinline__ void k3_epilogue(const Params& P, double* out_row, uint32_t* status, int slot, int a,
+                                            const K3AccS& A) {
     double* o = out_row + P.col_glcm + (slot * P.n_angles + a) * kNGlcm;
-    if (M == 0) { o[3] = 0.0; o[4] = 0.0; return; }
+    const long long M = A.s[7];
+    if (M == 0) {
+        o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 0.0; o[4] = 0.0; o[5] = 1.0;
+        if (status) atomicOr(status, kStNoPairs);
+        return;
+    }
+    // the walked pairs that do not exist added exactly 1.0 each to the homogeneity sum
+    const unsigned long long hom_true = A.hom - ((unsigned long long)((long long)A.np - M) << 40);
     const double Md = (double)M;
-    const double asmv = (double)(2ull * sold + (unsigned long long)M) / (Md * Md);
+    const long long Si = A.s[0], Sj = A.s[1], Sii = A.s[2], Sjj = A.s[3], Sij = A.s[4];
+    const long long vi = M * Sii - Si * Si, vj = M * Sjj - Sj * Sj, cov = M * Sij - Si * Sj;
+    const double asmv = (double)(2ull * (unsigned long long)A.s[6] + (unsigned long long)M) / (Md * Md);
+    o[0] = (double)(Sii + Sjj - 2 * Sij) / Md;
+    o[1] = (double)A.s[5] / Md;
+    o[2] = ((double)hom_true * 9.094947017729282e-13) / Md;
     o[3] = asmv;
     o[4] = sqrt(asmv);
+    o[5] = (vi == 0 || vj == 0) ? 1.0 : (double)cov / (sqrt((double)vi) * sqrt((double)vj));
 }
 
 template <bool MASKED, bool DUMP, int NG>
@@ -236,7 +256,8 @@ k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict
     const int id_sync = 1 + g, id_mine = 1 + NG + g, id_next = 1 + NG + (g + 1) % NG;
 
     for (int k = tid; k < 32768; k += kK3Threads) S.hist[k] = 0u;
-    if (tid < 4 * kMaxAngles * 2) (&S.acc[0][0][0])[tid] = 0u;
+    if (tid < 4 * 2 * kMaxAngles * (int)(sizeof(K3AccS) / 4)) reinterpret_cast<uint32_t*>(&S.acc[0][0][0])[tid] = 0u;
+    if (tid < 256) S.homtab[tid] = 1.0 / (1.0 + (double)(tid * tid));
     if (tid == 0) {
         for (int i = 0; i < 4 * kK3MaxStages; ++i) mbar_init(smem_addr(&S.full[0][0]) + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -282,17 +303,49 @@ k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict
             // ---- off the table: this direction's first items become hits in registers ----
             const K3Geom G = k3_geom(tw, P.dr[a], P.dc[a], bx[0], bx[1], bx[2], bx[3]);
             uint32_t hit[kCache][16];
-            uint32_t sold = 0u, mm = 0u, valid = 0u;
+            uint32_t sold = 0u, valid = 0u, np = 0u;
+            K3Acc A = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0};
+            K3AccS& Acc = S.acc[g][j & 1u][a];
+            auto sums16 = [&](const uint32_t (&I4)[4], const uint32_t (&J4)[4], uint32_t pm) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) k3_sums(S.homtab, I4[k], J4[k], k3_expand4(pm >> (4 * k)), A);
+                A.m += __popc(pm);
+                np += 16u;
+            };
+            // warp totals of the pair-stream sums into the group's accumulators
+            auto flush_sums = [&]() {
+                if (!__any_sync(0xffffffffu, np != 0u)) return;
+                const uint32_t r0 = __reduce_add_sync(0xffffffffu, A.si);
+                const uint32_t r1 = __reduce_add_sync(0xffffffffu, A.sj);
+                const uint32_t r2 = __reduce_add_sync(0xffffffffu, A.sii);
+                const uint32_t r3 = __reduce_add_sync(0xffffffffu, A.sjj);
+                const uint32_t r4 = __reduce_add_sync(0xffffffffu, A.sij);
+                const uint32_t r5 = __reduce_add_sync(0xffffffffu, A.sd);
+                const uint32_t r7 = __reduce_add_sync(0xffffffffu, A.m);
+                const uint32_t r8 = __reduce_add_sync(0xffffffffu, np);
+                // per-thread double sums (fixed order) are rounded to 2^-40 fixed point: the sums over lanes
+                // and warps are integer and do not depend on their order
+                const unsigned long long hf = warp_sum_redux((unsigned long long)__double2ll_rn(A.hom * 1099511627776.0));
+                if (lane == 0) {
+                    atomicAdd(&Acc.s[0], r0); atomicAdd(&Acc.s[1], r1); atomicAdd(&Acc.s[2], r2); atomicAdd(&Acc.s[3], r3);
+                    atomicAdd(&Acc.s[4], r4); atomicAdd(&Acc.s[5], r5); atomicAdd(&Acc.s[7], r7);
+                    atomicAdd(&Acc.np, r8);
+                    atomicAdd(&Acc.hom, hf);
+                }
+                A = K3Acc{0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0};
+                np = 0u;
+            };
 #pragma unroll
             for (int i = 0; i < kCache; ++i) {
                 const int item = gt + i * gthreads;
                 uint32_t I4[4], J4[4], pm;
                 if (item < G.items && k3_item16<MASKED>(Gp, G, item, I4, J4, pm)) {
+                    sums16(I4, J4, pm);
                     k3_hits16(I4, J4, pm, hit[i]);
-                    mm += __popc(pm);
                     valid |= 1u << i;
                 }
             }
+            flush_sums();
             bar_sync(id_mine, 2 * gthreads);               // ---- table owned by this group ----
 #pragma unroll
             for (int i = 0; i < kCache; ++i)
@@ -303,10 +356,10 @@ k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict
             for (int item = gt + kCache * gthreads; item < G.items; item += gthreads) {
                 uint32_t I4[4], J4[4], pm, h16[16];
                 if (k3_item16<MASKED>(Gp, G, item, I4, J4, pm)) {
+                    sums16(I4, J4, pm);
                     k3_hits16(I4, J4, pm, h16);
 #pragma unroll
                     for (int k = 0; k < 16; ++k) k3_hit(hist_addr, h16[k], sold);
-                    mm += __popc(pm);
                 }
             }
             bar_sync(id_sync, gthreads);                   // bins of this direction complete
@@ -337,9 +390,9 @@ k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict
             }
             // ---- hand the clean table on (the very last hand-over has no taker) ----
             if (!(g == NG - 1 && j + 1 == n_iter && a + 1 == P.n_angles)) bar_arrive(id_next, 2 * gthreads);
+            if (G.items > kCache * gthreads) flush_sums();  // items beyond the register cache
             const uint32_t so = __reduce_add_sync(0xffffffffu, sold);
-            const uint32_t mo = __reduce_add_sync(0xffffffffu, mm);
-            if (lane == 0 && mo) { atomicAdd(&S.acc[g][a][0], so); atomicAdd(&S.acc[g][a][1], mo); }
+            if (lane == 0 && so) atomicAdd(&Acc.s[6], so);
         }
         // next record (copy started ns rounds ago) must have landed before the group moves on
         const int s_next = s + 1 == ns ? 0 : s + 1;
@@ -347,11 +400,14 @@ k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict
         if (gt == 0 && j + 1 < my_count) mbar_wait(full0 + 8 * s_next, phase_next);
         bar_sync(id_sync, gthreads);                       // sums final, this record no longer read, next one visible
         if (active && gw < P.n_angles && lane == 0) {
-            double* out_row = P.out + (long long)(t / (uint32_t)P.c_out) * P.row_stride;
-            k3_epilogue(P, out_row, (int)(t % (uint32_t)P.c_out), gw, (unsigned long long)S.acc[g][gw][0],
-                        (long long)S.acc[g][gw][1]);
-            S.acc[g][gw][0] = 0u;
-            S.acc[g][gw][1] = 0u;
+            const uint32_t row = t / (uint32_t)P.c_out;
+            k3_epilogue(P, P.out + (long long)row * P.row_stride, P.status ? P.status + row : nullptr,
+                        (int)(t - row * (uint32_t)P.c_out), gw, S.acc[g][j & 1u][gw]);
+            K3AccS& Acc = S.acc[g][j & 1u][gw];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) Acc.s[k] = 0u;
+            Acc.hom = 0ull;
+            Acc.np = 0u;
         }
         if (gt == 0 && j + ns < my_count) fetch(t + (uint32_t)ns * t_step, s);
         s = s_next;

@@ -1,16 +1,11 @@
-// K3a: the four GLCM properties that are plain sums over the pair stream.
+// K3a: staging for the GLCM kernel -- tile maximum, 8-bit quantisation, mask bits and their bounding box.
 //
-// Replaces (together with k3_glcm.cuh) the reference's greycomatrix + greycoprops call
-// (channel_importance_hand_crafted_features.ipynb cell 13, NB:269-308).  contrast, dissimilarity,
-// homogeneity and correlation are linear in the co-occurrence matrix, so they need no matrix at all:
-//   contrast      = sum (i-j)^2 / M = (Sii + Sjj - 2 Sij) / M
-//   dissimilarity = sum |i-j| / M
-//   homogeneity   = sum 1/(1+(i-j)^2) / M         (256-entry table, 2^-40 fixed point => order-free)
-//   correlation   = (M Sij - Si Sj) / sqrt((M Sii - Si^2)(M Sjj - Sj^2))   (exact integers)
-// Only ASM / energy need the bins (kernel K3, the 128 KB table ring).
-//
-// One warp per tile, no CTA barrier, dynamic tile scheduling: the quantised tile lives in a per-warp
-// shared-memory buffer, every direction is one lane-strided pass over its pair groups.
+// Replaces the reference's (x / x.max()) * 255 -> uint8 step
+// (channel_importance_hand_crafted_features.ipynb cell 13, NB:293-295) and prepares what K3
+// (k3_glcm.cuh) needs per tile as one contiguous record: header (pair box, size), quantised bytes,
+// mask bits.  One warp per tile, no CTA barrier, dynamic tile scheduling; the record is assembled in
+// shared memory and leaves with a single bulk copy (cp.async.bulk shared -> global), so K3 can pull
+// it into its ring with a single bulk copy as well.
 #pragma once
 #include "k3_glcm.cuh"
 
@@ -19,24 +14,20 @@ namespace imfeat {
 constexpr int kK3aThreads = 32;
 
 __host__ __device__ inline size_t k3a_smem_bytes(int max_pixels, bool masked) {
-    return 256 * sizeof(double) + k3_rec_bytes(max_pixels, masked);
+    return k3_rec_bytes(max_pixels, masked);
 }
 
 template <bool MASKED>
 __global__ void __launch_bounds__(kK3aThreads, 16)
-k3a_glcm_sums_kernel(const __grid_constant__ Params P, unsigned char* __restrict__ recs, int max_pixels) {
+k3a_glcm_stage_kernel(const __grid_constant__ Params P, unsigned char* __restrict__ recs, int max_pixels) {
     extern __shared__ __align__(16) unsigned char k3a_raw[];
-    double* homtab = reinterpret_cast<double*>(k3a_raw);
-    // the tile's record is assembled in shared memory (K3a works on it) and stored with one bulk copy
-    unsigned char* rec = k3a_raw + 256 * sizeof(double);
+    unsigned char* rec = k3a_raw;
     K3RecHdr& Hd = *reinterpret_cast<K3RecHdr*>(rec);
     const uint32_t rec_bytes = (uint32_t)k3_rec_bytes(max_pixels, MASKED);
     K3Group Gp;
     Gp.q8 = reinterpret_cast<uint32_t*>(rec + sizeof(K3RecHdr));
     Gp.mbits = Gp.q8 + k3_q8_words(max_pixels);
     const int lane = threadIdx.x;
-    for (int k = lane; k < 256; k += 32) homtab[k] = 1.0 / (1.0 + (double)(k * k));
-    __syncwarp();
     const bool k1_max = P.col_basic >= 0;      // K1 (earlier launch, same stream) wrote the tile maximum
 
     for (long long t = next_tile(P.sched + 2); t < P.n_tiles; t = next_tile(P.sched + 2)) {
@@ -131,54 +122,6 @@ k3a_glcm_sums_kernel(const __grid_constant__ Params P, unsigned char* __restrict
         __syncwarp();
         if (lane == 0) bulk_s2g(recs + (size_t)t * rec_bytes, smem_addr(rec), rec_bytes);
 
-        // ---- 3. one lane-strided pass over the pair groups per direction ----
-        for (int a = 0; a < P.n_angles; ++a) {
-            const K3Geom G = k3_geom(T.w, P.dr[a], P.dc[a], bx[0], bx[1], bx[2], bx[3]);
-            K3Acc A0 = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0}, A1 = A0;   // two independent chains
-            uint32_t nproc = 0u;                           // items this lane went through
-            for (int item = lane; item < G.items; item += 32) {
-                uint32_t I4[4], J4[4], pm;
-                if (k3_item16<MASKED>(Gp, G, item, I4, J4, pm)) {
-                    k3_sums(homtab, I4[0], J4[0], k3_expand4(pm), A0);
-                    k3_sums(homtab, I4[1], J4[1], k3_expand4(pm >> 4), A1);
-                    k3_sums(homtab, I4[2], J4[2], k3_expand4(pm >> 8), A0);
-                    k3_sums(homtab, I4[3], J4[3], k3_expand4(pm >> 12), A1);
-                    A0.m += __popc(pm);
-                    ++nproc;
-                }
-            }
-            const uint32_t si = __reduce_add_sync(0xffffffffu, A0.si + A1.si);
-            const uint32_t sj = __reduce_add_sync(0xffffffffu, A0.sj + A1.sj);
-            const uint32_t sii = __reduce_add_sync(0xffffffffu, A0.sii + A1.sii);
-            const uint32_t sjj = __reduce_add_sync(0xffffffffu, A0.sjj + A1.sjj);
-            const uint32_t sij = __reduce_add_sync(0xffffffffu, A0.sij + A1.sij);
-            const uint32_t sd = __reduce_add_sync(0xffffffffu, A0.sd + A1.sd);
-            const uint32_t mm = __reduce_add_sync(0xffffffffu, A0.m + A1.m);
-            const uint32_t np = __reduce_add_sync(0xffffffffu, nproc);
-            // per-lane double sums (fixed lane-strided order) are rounded to 2^-40 fixed point, so the
-            // warp reduction is an integer sum and the result does not depend on which warp ran the tile
-            const unsigned long long homfix =
-                warp_sum_redux((unsigned long long)__double2ll_rn((A0.hom + A1.hom) * 1099511627776.0));
-            if (lane == 0) {
-                double* o = T.out_row + P.col_glcm + (T.slot * P.n_angles + a) * kNGlcm;
-                const long long M = mm;
-                if (M == 0) {
-                    o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[5] = 1.0;
-                    if (T.status) atomicOr(T.status, kStNoPairs);
-                } else {
-                    // the pairs of the processed items that do not exist added exactly 1.0 each
-                    const long long D = 16ll * np - M;
-                    const double Md = (double)M;
-                    const long long Si = si, Sj = sj, Sii = sii, Sjj = sjj, Sij = sij;
-                    o[0] = (double)(Sii + Sjj - 2 * Sij) / Md;
-                    o[1] = (double)sd / Md;
-                    o[2] = ((double)(homfix - ((unsigned long long)D << 40)) * 9.094947017729282e-13) / Md;
-                    const long long vi = M * Sii - Si * Si, vj = M * Sjj - Sj * Sj, cov = M * Sij - Si * Sj;
-                    o[5] = (vi == 0 || vj == 0) ? 1.0 : (double)cov / (sqrt((double)vi) * sqrt((double)vj));
-                }
-            }
-        }
-        __syncwarp();                                      // q8 / mbits are rewritten by the next tile
     }
     if (lane == 0) bulk_wait_all();
 }
