@@ -12,7 +12,6 @@
 #include "k1_moments.cuh"
 #include "k2_order_entropy.cuh"
 #include "k3_glcm.cuh"
-#include "k3a_stage.cuh"
 #include "k4_shape.cuh"
 
 using namespace imfeat;
@@ -29,8 +28,6 @@ struct imfeat_ctx {
     int device;
     int sm_count;
     int k1_bps[2], k4_bps[2], k2c_bps[2], k4w_bps[2];   // resident CTAs per SM (occupancy API), [masked]
-    cudaMemPool_t pool;         // stream-ordered scratch (K3 records); keeps its memory between calls
-    int k3a_bps[2], k3a_maxpx;                          // same for K3a, valid for k3a_maxpx (dynamic smem)
     unsigned int* d_sched;      // ring of kSchedSlots x 8 work counters (one slot per extract call)
     unsigned int sched_head;
     uint32_t* d_worklist;       // [0] = count, [1..] = tile ids left to the full-range K2 kernel
@@ -141,16 +138,6 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
         gfix[k] = (unsigned long long)llroundl((a - b) * 4398046511104.0L);
     }
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_sched, sizeof(unsigned int) * 8 * kSchedSlots);
-    if (e == cudaSuccess) {
-        cudaMemPoolProps props = {};
-        props.allocType = cudaMemAllocationTypePinned;
-        props.handleTypes = cudaMemHandleTypeNone;
-        props.location.type = cudaMemLocationTypeDevice;
-        props.location.id = device;
-        e = cudaMemPoolCreate(&ctx->pool, &props);
-        unsigned long long keep = ~0ull;
-        if (e == cudaSuccess) e = cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_gfix, sizeof(unsigned long long) * kMaxPixels);
     if (e == cudaSuccess)
         e = cudaMemcpy(ctx->d_gfix, gfix, sizeof(unsigned long long) * kMaxPixels, cudaMemcpyHostToDevice);
@@ -213,7 +200,6 @@ int imfeat_destroy(imfeat_ctx* ctx) {
     if (ctx->d_gfix) cudaFree(ctx->d_gfix);
     if (ctx->d_worklist) cudaFree(ctx->d_worklist);
     if (ctx->d_sched) cudaFree(ctx->d_sched);
-    if (ctx->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(ctx->pool); }
     free(ctx);
     return IMFEAT_OK;
 }
@@ -221,14 +207,13 @@ int imfeat_destroy(imfeat_ctx* ctx) {
 }  // extern "C"
 
 template <bool DUMP>
-static void launch_k3(bool masked, int ng, int grid, size_t smem, cudaStream_t st, const Params& P,
-                      const unsigned char* recs, int maxpx, int ns) {
+static void launch_k3(bool masked, int ng, int grid, size_t smem, cudaStream_t st, const Params& P, int maxpx) {
     if (ng == 4) {
-        if (masked) k3_glcm_kernel<true, DUMP, 4><<<grid, kK3Threads, smem, st>>>(P, recs, maxpx, ns);
-        else k3_glcm_kernel<false, DUMP, 4><<<grid, kK3Threads, smem, st>>>(P, recs, maxpx, ns);
+        if (masked) k3_glcm_kernel<true, DUMP, 4><<<grid, kK3Threads, smem, st>>>(P, maxpx);
+        else k3_glcm_kernel<false, DUMP, 4><<<grid, kK3Threads, smem, st>>>(P, maxpx);
     } else {
-        if (masked) k3_glcm_kernel<true, DUMP, 2><<<grid, kK3Threads, smem, st>>>(P, recs, maxpx, ns);
-        else k3_glcm_kernel<false, DUMP, 2><<<grid, kK3Threads, smem, st>>>(P, recs, maxpx, ns);
+        if (masked) k3_glcm_kernel<true, DUMP, 2><<<grid, kK3Threads, smem, st>>>(P, maxpx);
+        else k3_glcm_kernel<false, DUMP, 2><<<grid, kK3Threads, smem, st>>>(P, maxpx);
     }
 }
 
@@ -394,26 +379,9 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
     if (o->want_glcm) {
         const int g3 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
         const int maxpx = ((P.hs * P.ws + 7) & ~7);
-        // K3a: maximum, quantisation, mask bits (warp per tile); leaves one record per tile for K3 in a
-        // stream-ordered scratch buffer
-        const size_t smem_a = k3a_smem_bytes(maxpx, masked);
-        if (ctx->k3a_maxpx != maxpx) {
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k3a_bps[0], k3a_glcm_stage_kernel<false>, kK3aThreads, k3a_smem_bytes(maxpx, false)));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k3a_bps[1], k3a_glcm_stage_kernel<true>, kK3aThreads, k3a_smem_bytes(maxpx, true)));
-            ctx->k3a_maxpx = maxpx;
-        }
-        unsigned char* recs = nullptr;
-        CU(cudaMallocFromPoolAsync((void**)&recs, k3_rec_bytes(maxpx, masked) * (size_t)P.n_tiles, ctx->pool, st));
-        const long long resa = sm * (ctx->k3a_bps[masked] > 0 ? ctx->k3a_bps[masked] : 1);
-        const int ga = (int)(P.n_tiles < resa ? P.n_tiles : resa);
-        if (masked) k3a_glcm_stage_kernel<true><<<ga, kK3aThreads, smem_a, st>>>(P, recs, maxpx);
-        else k3a_glcm_stage_kernel<false><<<ga, kK3aThreads, smem_a, st>>>(P, recs, maxpx);
-        // K3: pair-stream sums and the bins on the shared-memory table, groups taking turns
-        const int ns3 = k3_stages(maxpx, masked);
-        launch_k3<false>(masked, k3_groups(maxpx, masked), g3, k3_smem_bytes(maxpx, masked), st, P, recs, maxpx, ns3);
-        CU(cudaFreeAsync(recs, st));
+        launch_k3<false>(masked, k3_groups(maxpx, masked), g3, k3_smem_bytes(maxpx, masked), st, P, maxpx);
         IMFEAT_MARK(2)
-        ctx->launches += 2;
+        ctx->launches += 1;
     }
     if (o->want_shape || o->want_moments) {
         const char* k4env = getenv("IMFEAT_K4_WARP");
@@ -510,18 +478,7 @@ int imfeat_glcm_counts_device(imfeat_ctx* ctx, const uint16_t* d_planes, const u
     const int g3 = (int)(P.n_tiles < ctx->sm_count ? P.n_tiles : ctx->sm_count);
     const int maxpx = ((P.hs * P.ws + 7) & ~7);
     const bool masked = d_masks != nullptr;
-    unsigned int* sched = ctx->d_sched + (size_t)(ctx->sched_head++ % kSchedSlots) * 8;
-    CU(cudaMemsetAsync(sched, 0, sizeof(unsigned int) * 8, st));
-    P.sched = sched;
-    unsigned char* recs = nullptr;
-    CU(cudaMallocFromPoolAsync((void**)&recs, k3_rec_bytes(maxpx, masked) * (size_t)P.n_tiles, ctx->pool, st));
-    const int ga = (int)(P.n_tiles < 16ll * ctx->sm_count ? P.n_tiles : 16ll * ctx->sm_count);
-    if (masked) k3a_glcm_stage_kernel<true><<<ga, kK3aThreads, k3a_smem_bytes(maxpx, true), st>>>(P, recs, maxpx);
-    else k3a_glcm_stage_kernel<false><<<ga, kK3aThreads, k3a_smem_bytes(maxpx, false), st>>>(P, recs, maxpx);
-    const int ns3 = k3_stages(maxpx, masked);
-    launch_k3<true>(masked, k3_groups(maxpx, masked), g3, k3_smem_bytes(maxpx, masked), st, P, recs, maxpx, ns3);
-    CU(cudaFreeAsync(recs, st));
-    ctx->launches += 1;
+    launch_k3<true>(masked, k3_groups(maxpx, masked), g3, k3_smem_bytes(maxpx, masked), st, P, maxpx);
     ctx->launches += 1;
     CU(cudaGetLastError());
     CU(cudaFreeAsync(scratch, st));

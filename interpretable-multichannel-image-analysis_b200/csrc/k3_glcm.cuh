@@ -7,9 +7,6 @@
 //
 // * quantiser: floor(255*x/max) with an exact multiply-shift reciprocal (bit-identical to the
 //   notebook's float64 expression for every uint16 pair; tests/test_oracle_cpu.py).
-// * two kernels.  K3a (k3a_stage.cuh, one warp per tile) finds the maximum, quantises the tile and
-//   leaves a per-tile record (header, quantised bytes, mask bits) in a scratch buffer.  K3 (this file)
-//   consumes the records: pair-stream sums and the bins.
 // * the 256x256 bins live in shared memory as 16-bit counters (two per 32-bit word, 128 KB), built
 //   with shared-memory atomics on the pair stream, dumped on request (parity), and only ever
 //   cleared sparsely by re-walking the pairs.  One persistent CTA per SM; its two 512-thread groups
@@ -17,8 +14,8 @@
 //   (bar.arrive / bar.sync: the waiting group is parked in hardware and issues nothing).  While one
 //   group owns the table the others load the pair items of their next direction, add up the pair-stream
 //   sums (contrast, dissimilarity, homogeneity, correlation need no bins) and turn the pairs into hits.
-// * records arrive through a shared-memory ring filled by cp.async.bulk (1-D TMA) completing on
-//   mbarriers, several tiles ahead, so staging costs no instructions.
+// * each group stages its own tile (maximum from K1's column when the basic block ran, mask bits and
+//   their bounding box, 8-bit quantisation into shared memory) while other groups use the table.
 // * ASM = sum_bins c^2 is accumulated from the atomics' return values
 //   (c^2 = sum_{k<c} (2k+1) = 2*sum(old) + c), so there is no pass over the bins.
 #pragma once
@@ -28,18 +25,13 @@ namespace imfeat {
 
 
 constexpr int kK3Threads = 1024;     // NG groups of 1024 / NG threads
-constexpr int kK3MaxStages = 4;      // records in flight per group
 
-// Per-tile record written by K3a and consumed by K3: 32-byte header, quantised pixels (one byte each,
-// row-major, + slack for unaligned 4-byte reads), mask bits (masked variant only).
-struct K3RecHdr {
-    int box[4];                      // rows [box0, box1], columns [box2, box3] that can hold pairs
-    int h, w, pad[2];
-};
+// per-group staging buffers behind K3Smem: quantised pixels (one byte each, row-major, + slack for the
+// 16-byte item reads) and mask bits (masked variant only)
 __host__ __device__ inline int k3_q8_words(int max_pixels) { return (max_pixels / 4 + 8 + 3) & ~3; }
 __host__ __device__ inline int k3_mb_words(int max_pixels, bool masked) { return masked ? ((max_pixels / 32 + 2 + 3) & ~3) : 0; }
-__host__ __device__ inline size_t k3_rec_bytes(int max_pixels, bool masked) {
-    return sizeof(K3RecHdr) + 4 * (size_t)(k3_q8_words(max_pixels) + k3_mb_words(max_pixels, masked));
+__host__ __device__ inline size_t k3_group_bytes(int max_pixels, bool masked) {
+    return 4 * (size_t)(k3_q8_words(max_pixels) + k3_mb_words(max_pixels, masked));
 }
 
 // per group and direction, summed over the warps of the group
@@ -50,26 +42,22 @@ struct K3AccS {
 };
 struct K3Smem {
     uint32_t hist[32768];
-    unsigned long long full[4][kK3MaxStages];   // mbarriers: record landed
     double homtab[256];                         // 1 / (1 + d^2)
     K3AccS acc[4][2][kMaxAngles];               // per group, tile parity (the epilogue of a tile overlaps the
                                                 // next tile's first sums) and direction
+    int box[4][2][4];                           // mask bounding box per group and tile parity: rmin rmax cmin cmax
+    uint32_t wmax[4][32];                       // per-warp maxima (only when K1 did not run)
 };
 struct K3Group {                               // where the quantised tile and its mask bits live
     uint32_t* q8;                              // quantised pixels (bytes) + slack for unaligned reads
     uint32_t* mbits;                           // one bit per pixel: inside the mask (masked variant)
 };
-// groups sharing the table (4, or 2 when the records are too large for four rings) and ring depth
+// groups sharing the table: 4, or 2 when four staging buffers do not fit
 __host__ __device__ inline int k3_groups(int max_pixels, bool masked) {
-    return 4 * k3_rec_bytes(max_pixels, masked) <= 227 * 1024 - sizeof(K3Smem) ? 4 : 2;
-}
-__host__ __device__ inline int k3_stages(int max_pixels, bool masked) {
-    const size_t room = 227 * 1024 - sizeof(K3Smem);
-    const size_t ns = room / (k3_groups(max_pixels, masked) * k3_rec_bytes(max_pixels, masked));
-    return ns > (size_t)kK3MaxStages ? kK3MaxStages : (int)ns;
+    return sizeof(K3Smem) + 4 * k3_group_bytes(max_pixels, masked) <= 227 * 1024 ? 4 : 2;
 }
 __host__ __device__ inline size_t k3_smem_bytes(int max_pixels, bool masked) {
-    return sizeof(K3Smem) + (size_t)k3_groups(max_pixels, masked) * k3_stages(max_pixels, masked) * k3_rec_bytes(max_pixels, masked);
+    return sizeof(K3Smem) + (size_t)k3_groups(max_pixels, masked) * k3_group_bytes(max_pixels, masked);
 }
 
 struct K3Acc {
@@ -241,28 +229,27 @@ __device__ __forceinline__ void k3_epilogue(const Params& P, double* out_row, ui
 
 template <bool MASKED, bool DUMP, int NG>
 __global__ void __launch_bounds__(kK3Threads, 1)
-k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict__ recs, int max_pixels, int ns) {
+k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels) {
     extern __shared__ __align__(16) unsigned char k3_smem_raw[];
     K3Smem& S = *reinterpret_cast<K3Smem*>(k3_smem_raw);
     constexpr int gthreads = kK3Threads / NG;
     constexpr int kCache = 256 / gthreads + (gthreads > 256 ? 1 : 0);   // items (16 pairs each) per thread held in registers
     const int tid = threadIdx.x, lane = tid & 31;
     const int g = tid / gthreads, gt = tid % gthreads, gw = gt >> 5;
-    const uint32_t rec_bytes = (uint32_t)k3_rec_bytes(max_pixels, MASKED);
-    const int q8w = k3_q8_words(max_pixels);
-    unsigned char* stage0 = k3_smem_raw + sizeof(K3Smem) + (size_t)g * ns * rec_bytes;
-    const uint32_t full0 = smem_addr(&S.full[g][0]);
+    K3Group Gp;
+    Gp.q8 = reinterpret_cast<uint32_t*>(k3_smem_raw + sizeof(K3Smem) + (size_t)g * k3_group_bytes(max_pixels, MASKED));
+    Gp.mbits = Gp.q8 + k3_q8_words(max_pixels);
     const uint32_t hist_addr = smem_addr(S.hist);
     const int id_sync = 1 + g, id_mine = 1 + NG + g, id_next = 1 + NG + (g + 1) % NG;
 
     for (int k = tid; k < 32768; k += kK3Threads) S.hist[k] = 0u;
     if (tid < 4 * 2 * kMaxAngles * (int)(sizeof(K3AccS) / 4)) reinterpret_cast<uint32_t*>(&S.acc[0][0][0])[tid] = 0u;
     if (tid < 256) S.homtab[tid] = 1.0 / (1.0 + (double)(tid * tid));
-    if (tid == 0) {
-        for (int i = 0; i < 4 * kK3MaxStages; ++i) mbar_init(smem_addr(&S.full[0][0]) + 8 * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    if (tid < 8) { S.box[tid >> 1][tid & 1][0] = 1 << 30; S.box[tid >> 1][tid & 1][1] = -1; S.box[tid >> 1][tid & 1][2] = 1 << 30; S.box[tid >> 1][tid & 1][3] = -1; }
     __syncthreads();
+    // K1 (same stream, earlier launch) already wrote the tile maximum into the table when the basic
+    // block is requested; then the max pass and its barrier are skipped.
+    const bool k1_max = P.col_basic >= 0;
 
     // tiles of this CTA: blockIdx.x + k * gridDim.x; group g takes k = NG * j + g
     const uint32_t n_tiles = (uint32_t)P.n_tiles, first = blockIdx.x;
@@ -270,32 +257,112 @@ k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict
     const uint32_t n_iter = (mine + NG - 1) / NG;          // every group runs the same number of rounds
     const uint32_t my_count = (mine + NG - 1 - g) / NG;
     const uint32_t t_step = NG * gridDim.x;
-    auto fetch = [&](uint32_t tile, int s) {               // one thread: start the bulk copy of a record
-        mbar_expect_tx(full0 + 8 * s, rec_bytes);
-        bulk_g2s(smem_addr(stage0 + (size_t)s * rec_bytes), recs + (size_t)tile * rec_bytes, rec_bytes, full0 + 8 * s);
-    };
     uint32_t t = first + g * gridDim.x;                    // this round's tile
-    if (gt == 0) {
-        for (uint32_t j = 0; j < (uint32_t)ns && j < my_count; ++j) fetch(t + j * t_step, (int)j);
-        if (my_count) mbar_wait(full0, 0u);
-    }
     if (g == NG - 1) bar_arrive(1 + NG, 2 * gthreads);     // the table starts out free for group 0
-    bar_sync(id_sync, gthreads);                           // first record visible to the group
 
-    int s = 0;
-    uint32_t phase = 0u;
     for (uint32_t j = 0; j < n_iter; ++j, t += t_step) {
         const bool active = j < my_count;
-        const unsigned char* rec = stage0 + (size_t)s * rec_bytes;
-        K3Group Gp;
-        Gp.q8 = reinterpret_cast<uint32_t*>(const_cast<unsigned char*>(rec) + sizeof(K3RecHdr));
-        Gp.mbits = Gp.q8 + q8w;
-        int bx[4] = {0, -1, 0, -1}, tw = 0;
+        const int buf = (int)(j & 1u);
+        int tw = 0, th = 0;
         if (active) {
-            const K3RecHdr& Hd = *reinterpret_cast<const K3RecHdr*>(rec);
-            bx[0] = Hd.box[0]; bx[1] = Hd.box[1]; bx[2] = Hd.box[2]; bx[3] = Hd.box[3];
-            tw = Hd.w;
+            const Tile T = resolve_tile(P, t);
+            tw = T.w; th = T.h;
+            const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
+            const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
+            const int nfull = T.n >> 3, rem = T.n & 7;
+            uint8_t* mbytes = reinterpret_cast<uint8_t*>(Gp.mbits);
+
+            // ---- 1. tile maximum (over the mask when masked); stage the mask bits and their bounding box ----
+            uint32_t mx2 = 0u;
+            int brmin = 1 << 30, brmax = -1, bcmin = 1 << 30, bcmax = -1;
+            double vmaxd = 0.0;
+            if (k1_max) vmaxd = T.out_row[P.col_basic + kNBasic * T.slot + 10];
+            for (int idx = gt; idx < nfull && (MASKED || !k1_max); idx += gthreads) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (!k1_max) v = ld_reuse(px4 + idx);
+                if (MASKED) {
+                    const uint2 m = __ldg(mk2 + idx);
+                    const uint32_t c0 = __vcmpne4(m.x, 0u), c1 = __vcmpne4(m.y, 0u);
+                    // 8 mask bytes -> 8 bits (byte k -> bit k)
+                    const uint32_t b0 = ((c0 & 0x01010101u) * 0x01020408u) >> 24;
+                    const uint32_t b1 = ((c1 & 0x01010101u) * 0x01020408u) >> 24;
+                    const uint32_t bits8 = (b0 & 0xfu) | ((b1 & 0xfu) << 4);
+                    mbytes[idx] = (uint8_t)bits8;
+                    if (bits8) {
+                        const int p0 = 8 * idx, ra = p0 / T.w, ca = p0 - ra * T.w;
+                        if (ca + 7 < T.w) {                // the 8 pixels lie in one row
+                            brmin = min(brmin, ra); brmax = max(brmax, ra);
+                            bcmin = min(bcmin, ca + __ffs(bits8) - 1); bcmax = max(bcmax, ca + 31 - __clz(bits8));
+                        } else {                           // straddles rows: be conservative
+                            brmin = min(brmin, ra); brmax = max(brmax, (p0 + 7) / T.w);
+                            bcmin = 0; bcmax = T.w - 1;
+                        }
+                    }
+                    v.x &= __byte_perm(c0, 0u, 0x1100); v.y &= __byte_perm(c0, 0u, 0x3322);
+                    v.z &= __byte_perm(c1, 0u, 0x1100); v.w &= __byte_perm(c1, 0u, 0x3322);
+                }
+                mx2 = __vmaxu2(mx2, __vmaxu2(__vmaxu2(v.x, v.y), __vmaxu2(v.z, v.w)));
+            }
+            if (gt == 0 && rem) {                          // tail pixels (< 8): one thread, in order
+                uint32_t bits = 0u;
+                for (int k = 0; k < rem; ++k) {
+                    const int i = nfull * 8 + k;
+                    const bool ok = !MASKED || T.mk[i] != 0;
+                    if (ok) {
+                        bits |= 1u << k;
+                        if (!k1_max) mx2 = __vmaxu2(mx2, (uint32_t)T.px[i]);
+                        const int ra = i / T.w, ca = i - ra * T.w;
+                        brmin = min(brmin, ra); brmax = max(brmax, ra); bcmin = min(bcmin, ca); bcmax = max(bcmax, ca);
+                    }
+                }
+                if (MASKED) mbytes[nfull] = (uint8_t)bits;
+            }
+            if (MASKED) {
+                brmin = __reduce_min_sync(0xffffffffu, brmin); brmax = __reduce_max_sync(0xffffffffu, brmax);
+                bcmin = __reduce_min_sync(0xffffffffu, bcmin); bcmax = __reduce_max_sync(0xffffffffu, bcmax);
+                if (lane == 0 && brmax >= 0) {
+                    atomicMin(&S.box[g][buf][0], brmin); atomicMax(&S.box[g][buf][1], brmax);
+                    atomicMin(&S.box[g][buf][2], bcmin); atomicMax(&S.box[g][buf][3], bcmax);
+                }
+            }
+            uint32_t vmax;
+            if (k1_max) {
+                vmax = (vmaxd == vmaxd) ? (uint32_t)vmaxd : 0u;      // NaN: empty mask, no pair exists anyway
+            } else {
+                const uint32_t wm = __reduce_max_sync(0xffffffffu, max(mx2 & 0xffffu, mx2 >> 16));
+                if (lane == 0) S.wmax[g][gw] = wm;
+                bar_sync(id_sync, gthreads);
+                vmax = lane < gthreads / 32 ? S.wmax[g][lane] : 0u;
+                vmax = __reduce_max_sync(0xffffffffu, vmax);
+            }
+
+            // ---- 2. quantise to 8 bits into shared memory ----
+            uint32_t mul = 0, sh = 24;
+            if (lane == 0) k3_magic(vmax, mul, sh);
+            mul = __shfl_sync(0xffffffffu, mul, 0);
+            sh = __shfl_sync(0xffffffffu, sh, 0);
+            for (int idx = gt; idx < nfull; idx += gthreads) {
+                const uint4 v = ld_reuse(px4 + idx);
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                uint32_t q[2] = {0u, 0u};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // pixels outside the mask may exceed vmax; they never enter a pair, clamp them
+                    uint32_t a = k3_quant(w4[k] & 0xffffu, mul, sh), b = k3_quant(w4[k] >> 16, mul, sh);
+                    if (MASKED) { a = min(a, 255u); b = min(b, 255u); }
+                    q[k >> 1] |= (a | (b << 8)) << (16 * (k & 1));
+                }
+                *reinterpret_cast<uint2*>(Gp.q8 + 2 * idx) = make_uint2(q[0], q[1]);
+            }
+            if (gt < rem) {
+                const int i = nfull * 8 + gt;
+                reinterpret_cast<uint8_t*>(Gp.q8)[i] = (uint8_t)min(k3_quant(T.px[i], mul, sh), 255u);
+            }
         }
+        bar_sync(id_sync, gthreads);                       // this tile staged
+        // box of pixels that can take part in a pair: the tile, or the mask's bounding box
+        int bx[4] = {0, th - 1, 0, tw - 1};
+        if (MASKED && active) { bx[0] = S.box[g][buf][0]; bx[1] = S.box[g][buf][1]; bx[2] = S.box[g][buf][2]; bx[3] = S.box[g][buf][3]; }
 
 #pragma unroll
         for (int a = 0; a < kMaxAngles; ++a) {
@@ -305,7 +372,7 @@ k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict
             uint32_t hit[kCache][16];
             uint32_t sold = 0u, valid = 0u, np = 0u;
             K3Acc A = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0};
-            K3AccS& Acc = S.acc[g][j & 1u][a];
+            K3AccS& Acc = S.acc[g][buf][a];
             auto sums16 = [&](const uint32_t (&I4)[4], const uint32_t (&J4)[4], uint32_t pm) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) k3_sums(S.homtab, I4[k], J4[k], k3_expand4(pm >> (4 * k)), A);
@@ -394,24 +461,20 @@ k3_glcm_kernel(const __grid_constant__ Params P, const unsigned char* __restrict
             const uint32_t so = __reduce_add_sync(0xffffffffu, sold);
             if (lane == 0 && so) atomicAdd(&Acc.s[6], so);
         }
-        // next record (copy started ns rounds ago) must have landed before the group moves on
-        const int s_next = s + 1 == ns ? 0 : s + 1;
-        const uint32_t phase_next = s + 1 == ns ? phase ^ 1u : phase;
-        if (gt == 0 && j + 1 < my_count) mbar_wait(full0 + 8 * s_next, phase_next);
-        bar_sync(id_sync, gthreads);                       // sums final, this record no longer read, next one visible
+        bar_sync(id_sync, gthreads);                       // sums final, staging buffers free
         if (active && gw < P.n_angles && lane == 0) {
             const uint32_t row = t / (uint32_t)P.c_out;
             k3_epilogue(P, P.out + (long long)row * P.row_stride, P.status ? P.status + row : nullptr,
-                        (int)(t - row * (uint32_t)P.c_out), gw, S.acc[g][j & 1u][gw]);
-            K3AccS& Acc = S.acc[g][j & 1u][gw];
+                        (int)(t - row * (uint32_t)P.c_out), gw, S.acc[g][buf][gw]);
+            K3AccS& Acc = S.acc[g][buf][gw];
 #pragma unroll
             for (int k = 0; k < 8; ++k) Acc.s[k] = 0u;
             Acc.hom = 0ull;
             Acc.np = 0u;
         }
-        if (gt == 0 && j + ns < my_count) fetch(t + (uint32_t)ns * t_step, s);
-        s = s_next;
-        phase = phase_next;
+        if (MASKED && active && gt == 0) {
+            S.box[g][buf][0] = 1 << 30; S.box[g][buf][1] = -1; S.box[g][buf][2] = 1 << 30; S.box[g][buf][3] = -1;
+        }
     }
 }
 
