@@ -209,11 +209,11 @@ int imfeat_destroy(imfeat_ctx* ctx) {
 template <bool DUMP>
 static void launch_k3(bool masked, int ng, int grid, size_t smem, cudaStream_t st, const Params& P, int maxpx) {
     if (ng == 4) {
-        if (masked) k3_glcm_kernel<true, DUMP, 4><<<grid, kK3Threads, smem, st>>>(P, maxpx);
-        else k3_glcm_kernel<false, DUMP, 4><<<grid, kK3Threads, smem, st>>>(P, maxpx);
+        if (masked) k3_glcm_kernel<true, DUMP, 4><<<grid, kK3Threads, smem, st>>>(P, maxpx, k3_prefetch(maxpx, masked) ? 1 : 0);
+        else k3_glcm_kernel<false, DUMP, 4><<<grid, kK3Threads, smem, st>>>(P, maxpx, k3_prefetch(maxpx, masked) ? 1 : 0);
     } else {
-        if (masked) k3_glcm_kernel<true, DUMP, 2><<<grid, kK3Threads, smem, st>>>(P, maxpx);
-        else k3_glcm_kernel<false, DUMP, 2><<<grid, kK3Threads, smem, st>>>(P, maxpx);
+        if (masked) k3_glcm_kernel<true, DUMP, 2><<<grid, kK3Threads, smem, st>>>(P, maxpx, k3_prefetch(maxpx, masked) ? 1 : 0);
+        else k3_glcm_kernel<false, DUMP, 2><<<grid, kK3Threads, smem, st>>>(P, maxpx, k3_prefetch(maxpx, masked) ? 1 : 0);
     }
 }
 

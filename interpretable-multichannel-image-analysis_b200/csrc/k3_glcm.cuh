@@ -15,7 +15,9 @@
 //   group owns the table the others load the pair items of their next direction, add up the pair-stream
 //   sums (contrast, dissimilarity, homogeneity, correlation need no bins) and turn the pairs into hits.
 // * each group stages its own tile (maximum from K1's column when the basic block ran, mask bits and
-//   their bounding box, 8-bit quantisation into shared memory) while other groups use the table.
+//   their bounding box, 8-bit quantisation into shared memory) while other groups use the table.  The
+//   raw pixels and mask bytes of a group's next tile are prefetched into shared memory with cp.async
+//   while it works on the current one, so staging never waits for global memory.
 // * ASM = sum_bins c^2 is accumulated from the atomics' return values
 //   (c^2 = sum_{k<c} (2k+1) = 2*sum(old) + c), so there is no pass over the bins.
 #pragma once
@@ -33,11 +35,21 @@ __host__ __device__ inline int k3_mb_words(int max_pixels, bool masked) { return
 __host__ __device__ inline size_t k3_group_bytes(int max_pixels, bool masked) {
     return 4 * (size_t)(k3_q8_words(max_pixels) + k3_mb_words(max_pixels, masked));
 }
+// prefetch buffer of a group: the next tile's raw pixels, then its mask bytes (max_pixels is a multiple of 8)
+__host__ __device__ inline size_t k3_raw_bytes(int max_pixels, bool masked) {
+    return (size_t)max_pixels * 2 + (masked ? (size_t)max_pixels : 0);
+}
 
+// What the first warp of a group announces about the group's next tile while the current one is under way.
+struct K3TileInfo {
+    int h, w;
+    uint32_t row, slot;              // output row, channel slot
+    uint32_t mul, sh, fast, pad;     // quantiser constants (k3_magic / k3_magic_fast) when K1's maximum is known
+};
 // per group and direction, summed over the warps of the group
 struct K3AccS {
     uint32_t s[8];                   // si sj sii sjj sij sd sold m
-    unsigned long long hom;          // sum of 1 / (1 + d^2) in 2^-40 fixed point
+    uint32_t hom_lo, hom_hi;         // sum of 1 / (1 + d^2) in 2^-40 fixed point (64-bit shared atomics are CAS loops)
     uint32_t np, pad;                // pairs walked (16 per item), existing or not
 };
 struct K3Smem {
@@ -47,6 +59,7 @@ struct K3Smem {
                                                 // next tile's first sums) and direction
     int box[4][2][4];                           // mask bounding box per group and tile parity: rmin rmax cmin cmax
     uint32_t wmax[4][32];                       // per-warp maxima (only when K1 did not run)
+    K3TileInfo info[4][2];                      // per group and tile parity
 };
 struct K3Group {                               // where the quantised tile and its mask bits live
     uint32_t* q8;                              // quantised pixels (bytes) + slack for unaligned reads
@@ -56,9 +69,23 @@ struct K3Group {                               // where the quantised tile and i
 __host__ __device__ inline int k3_groups(int max_pixels, bool masked) {
     return sizeof(K3Smem) + 4 * k3_group_bytes(max_pixels, masked) <= 227 * 1024 ? 4 : 2;
 }
-__host__ __device__ inline size_t k3_smem_bytes(int max_pixels, bool masked) {
-    return sizeof(K3Smem) + (size_t)k3_groups(max_pixels, masked) * k3_group_bytes(max_pixels, masked);
+// whether the raw-tile prefetch buffers fit next to the table
+__host__ __device__ inline bool k3_prefetch(int max_pixels, bool masked) {
+    const int ng = k3_groups(max_pixels, masked);
+    return sizeof(K3Smem) + ng * (k3_group_bytes(max_pixels, masked) + k3_raw_bytes(max_pixels, masked)) <= 227 * 1024;
 }
+__host__ __device__ inline size_t k3_smem_bytes(int max_pixels, bool masked) {
+    const int ng = k3_groups(max_pixels, masked);
+    return sizeof(K3Smem) + (size_t)ng * (k3_group_bytes(max_pixels, masked) +
+                                          (k3_prefetch(max_pixels, masked) ? k3_raw_bytes(max_pixels, masked) : 0));
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 struct K3Acc {
     uint32_t si, sj, sii, sjj, sij, sd, sasm, m;
@@ -78,6 +105,13 @@ __device__ __forceinline__ void k3_magic(uint32_t vmax, uint32_t& mul, uint32_t&
     while ((unsigned long long)(m - 1) * vmax >= two) --m;
     mul = m;
 }
+// 256 < vmax <= 4103: floor(255*x / vmax) = umulhi(x, 255 * ceil(2^32 / vmax)) for 0 <= x <= vmax
+// (255 * vmax^2 < 2^32 bounds the rounding error; checked exhaustively in tests/test_oracle_cpu.py)
+__device__ __forceinline__ bool k3_magic_fast(uint32_t vmax, uint32_t& mul) {
+    if (vmax <= 256u || vmax > 4103u) return false;
+    mul = 255u * (0xffffffffu / vmax + 1u);       // vmax is not a power of two here or the +1 is harmless: see test
+    return true;
+}
 __device__ __forceinline__ uint32_t k3_quant(uint32_t x, uint32_t mul, uint32_t sh) {
     return (uint32_t)(((unsigned long long)(x * 255u) * mul) >> sh);
 }
@@ -96,7 +130,7 @@ __device__ __forceinline__ uint32_t k3_bits16(const uint32_t* b, int off) {
 // of both pixel runs are loaded once and funnel-shifted into place.
 struct K3Geom {
     int nrows, r0, c0, c1, ipr, items, w, doff;
-    uint32_t rcp;                                  // floor(2^32 / ipr) + 1: row = umulhi(item, rcp)
+    float rcp;                                     // 1 / ipr: row = floor((item + 0.5) * rcp), exact for item < 2^20
 };
 // Pairs (r, c) -> (r + dr, c + dc) with both pixels inside the box rows [br0, br1], columns
 // [bc0, bc1] (the whole tile, or the bounding box of the mask: pairs outside it cannot exist).
@@ -108,9 +142,9 @@ __device__ __forceinline__ K3Geom k3_geom(int w, int dr, int dc, int br0, int br
     G.c1 = bc1 + 1 - (dc > 0 ? dc : 0);
     G.w = w;
     G.doff = dr * w + dc;
-    if (G.nrows <= 0 || G.c1 <= G.c0) { G.items = 0; G.ipr = 1; G.rcp = 0u; G.nrows = 0; return G; }
+    if (G.nrows <= 0 || G.c1 <= G.c0) { G.items = 0; G.ipr = 1; G.rcp = 1.0f; G.nrows = 0; return G; }
     G.ipr = (G.c1 - G.c0 + 15) >> 4;               // items per row
-    G.rcp = G.ipr > 1 ? 0xffffffffu / (uint32_t)G.ipr + 1u : 0u;
+    G.rcp = __frcp_rn((float)G.ipr);
     G.items = G.nrows * G.ipr;
     return G;
 }
@@ -121,7 +155,7 @@ __device__ __forceinline__ K3Geom k3_geom(int w, int dr, int dc, int br0, int br
 template <bool MASKED>
 __device__ __forceinline__ bool k3_item16(const K3Group& Gp, const K3Geom& G, int item, uint32_t (&I4)[4],
                                           uint32_t (&J4)[4], uint32_t& pm) {
-    const int r = G.ipr > 1 ? (int)__umulhi((uint32_t)item, G.rcp) : item;
+    const int r = (int)(((float)item + 0.5f) * G.rcp);
     const int c = G.c0 + 16 * (item - r * G.ipr);
     const int nv = min(16, G.c1 - c);
     const int oi = (G.r0 + r) * G.w + c, oj = oi + G.doff;
@@ -214,7 +248,7 @@ __device__ __forceinline__ void k3_epilogue(const Params& P, double* out_row, ui
         return;
     }
     // the walked pairs that do not exist added exactly 1.0 each to the homogeneity sum
-    const unsigned long long hom_true = A.hom - ((unsigned long long)((long long)A.np - M) << 40);
+    const unsigned long long hom_true = ((unsigned long long)A.hom_hi << 32 | A.hom_lo) - ((unsigned long long)((long long)A.np - M) << 40);
     const double Md = (double)M;
     const long long Si = A.s[0], Sj = A.s[1], Sii = A.s[2], Sjj = A.s[3], Sij = A.s[4];
     const long long vi = M * Sii - Si * Si, vj = M * Sjj - Sj * Sj, cov = M * Sij - Si * Sj;
@@ -229,7 +263,7 @@ __device__ __forceinline__ void k3_epilogue(const Params& P, double* out_row, ui
 
 template <bool MASKED, bool DUMP, int NG>
 __global__ void __launch_bounds__(kK3Threads, 1)
-k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels) {
+k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
     extern __shared__ __align__(16) unsigned char k3_smem_raw[];
     K3Smem& S = *reinterpret_cast<K3Smem*>(k3_smem_raw);
     constexpr int gthreads = kK3Threads / NG;
@@ -239,6 +273,9 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels) {
     K3Group Gp;
     Gp.q8 = reinterpret_cast<uint32_t*>(k3_smem_raw + sizeof(K3Smem) + (size_t)g * k3_group_bytes(max_pixels, MASKED));
     Gp.mbits = Gp.q8 + k3_q8_words(max_pixels);
+    // raw prefetch buffers lie behind the staging buffers of all groups
+    unsigned char* raw = k3_smem_raw + sizeof(K3Smem) + (size_t)NG * k3_group_bytes(max_pixels, MASKED) +
+                         (size_t)g * k3_raw_bytes(max_pixels, MASKED);
     const uint32_t hist_addr = smem_addr(S.hist);
     const int id_sync = 1 + g, id_mine = 1 + NG + g, id_next = 1 + NG + (g + 1) % NG;
 
@@ -259,29 +296,66 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels) {
     const uint32_t t_step = NG * gridDim.x;
     uint32_t t = first + g * gridDim.x;                    // this round's tile
     if (g == NG - 1) bar_arrive(1 + NG, 2 * gthreads);     // the table starts out free for group 0
+    // The first warp of a group announces the group's next tile while the current one is under way: it
+    // starts the copy of the raw pixels and mask bytes into the prefetch buffer, notes the geometry,
+    // and fetches K1's maximum, from which lane 0 derives the quantiser constants before the
+    // end-of-tile barrier (publish).
+    double vnext = 0.0;
+    auto announce = [&](uint32_t tile, int nb) {
+        const Tile T = resolve_tile(P, tile);
+        if (prefetch) {
+            const int n16 = (T.n * 2 + 15) >> 4, n8 = (T.n + 7) >> 3;
+            for (int k = lane; k < n16; k += 32) cp_async16(raw + 16 * k, reinterpret_cast<const unsigned char*>(T.px) + 16 * k);
+            if (MASKED)
+                for (int k = lane; k < n8; k += 32) cp_async8(raw + 2 * (size_t)max_pixels + 8 * k, T.mk + 8 * k);
+        }
+        if (lane == 0) {
+            K3TileInfo& I = S.info[g][nb];
+            I.h = T.h; I.w = T.w; I.slot = (uint32_t)T.slot; I.row = tile / (uint32_t)P.c_out;
+            if (k1_max) vnext = T.out_row[P.col_basic + kNBasic * T.slot + 10];
+        }
+    };
+    auto publish = [&](int nb) {                           // lane 0 of the first warp
+        if (!k1_max) return;
+        K3TileInfo& I = S.info[g][nb];
+        const uint32_t vmax = (vnext == vnext) ? (uint32_t)vnext : 0u;   // NaN: empty mask, no pair exists anyway
+        uint32_t mul = 0u, sh = 24u;
+        const bool fast = k3_magic_fast(vmax, mul);
+        if (!fast) k3_magic(vmax, mul, sh);
+        I.mul = mul; I.sh = sh; I.fast = fast ? 1u : 0u;
+    };
+    if (gw == 0 && my_count) {
+        announce(t, 0);
+        cp_async_wait_all();
+        if (lane == 0) publish(0);
+    }
+    bar_sync(id_sync, gthreads);
 
     for (uint32_t j = 0; j < n_iter; ++j, t += t_step) {
         const bool active = j < my_count;
         const int buf = (int)(j & 1u);
         int tw = 0, th = 0;
         if (active) {
-            const Tile T = resolve_tile(P, t);
-            tw = T.w; th = T.h;
-            const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
-            const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
-            const int nfull = T.n >> 3, rem = T.n & 7;
+            const K3TileInfo& I = S.info[g][buf];
+            tw = I.w; th = I.h;
+            const int tn = th * tw;
+            // pixels and mask bytes: from the prefetch buffer, or straight from global memory
+            const uint16_t* pxs = reinterpret_cast<const uint16_t*>(raw);
+            const uint8_t* mks = raw + 2 * (size_t)max_pixels;
+            if (!prefetch) { const Tile T = resolve_tile(P, t); pxs = T.px; mks = T.mk; }
+            const uint4* px4 = reinterpret_cast<const uint4*>(pxs);
+            const uint2* mk2 = reinterpret_cast<const uint2*>(mks);
+            const int nfull = tn >> 3, rem = tn & 7;
             uint8_t* mbytes = reinterpret_cast<uint8_t*>(Gp.mbits);
 
             // ---- 1. tile maximum (over the mask when masked); stage the mask bits and their bounding box ----
             uint32_t mx2 = 0u;
             int brmin = 1 << 30, brmax = -1, bcmin = 1 << 30, bcmax = -1;
-            double vmaxd = 0.0;
-            if (k1_max) vmaxd = T.out_row[P.col_basic + kNBasic * T.slot + 10];
             for (int idx = gt; idx < nfull && (MASKED || !k1_max); idx += gthreads) {
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (!k1_max) v = ld_reuse(px4 + idx);
+                if (!k1_max) v = px4[idx];
                 if (MASKED) {
-                    const uint2 m = __ldg(mk2 + idx);
+                    const uint2 m = mk2[idx];
                     const uint32_t c0 = __vcmpne4(m.x, 0u), c1 = __vcmpne4(m.y, 0u);
                     // 8 mask bytes -> 8 bits (byte k -> bit k)
                     const uint32_t b0 = ((c0 & 0x01010101u) * 0x01020408u) >> 24;
@@ -289,13 +363,13 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels) {
                     const uint32_t bits8 = (b0 & 0xfu) | ((b1 & 0xfu) << 4);
                     mbytes[idx] = (uint8_t)bits8;
                     if (bits8) {
-                        const int p0 = 8 * idx, ra = p0 / T.w, ca = p0 - ra * T.w;
-                        if (ca + 7 < T.w) {                // the 8 pixels lie in one row
+                        const int p0 = 8 * idx, ra = p0 / tw, ca = p0 - ra * tw;
+                        if (ca + 7 < tw) {                 // the 8 pixels lie in one row
                             brmin = min(brmin, ra); brmax = max(brmax, ra);
                             bcmin = min(bcmin, ca + __ffs(bits8) - 1); bcmax = max(bcmax, ca + 31 - __clz(bits8));
                         } else {                           // straddles rows: be conservative
-                            brmin = min(brmin, ra); brmax = max(brmax, (p0 + 7) / T.w);
-                            bcmin = 0; bcmax = T.w - 1;
+                            brmin = min(brmin, ra); brmax = max(brmax, (p0 + 7) / tw);
+                            bcmin = 0; bcmax = tw - 1;
                         }
                     }
                     v.x &= __byte_perm(c0, 0u, 0x1100); v.y &= __byte_perm(c0, 0u, 0x3322);
@@ -307,11 +381,11 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels) {
                 uint32_t bits = 0u;
                 for (int k = 0; k < rem; ++k) {
                     const int i = nfull * 8 + k;
-                    const bool ok = !MASKED || T.mk[i] != 0;
+                    const bool ok = !MASKED || mks[i] != 0;
                     if (ok) {
                         bits |= 1u << k;
-                        if (!k1_max) mx2 = __vmaxu2(mx2, (uint32_t)T.px[i]);
-                        const int ra = i / T.w, ca = i - ra * T.w;
+                        if (!k1_max) mx2 = __vmaxu2(mx2, (uint32_t)pxs[i]);
+                        const int ra = i / tw, ca = i - ra * tw;
                         brmin = min(brmin, ra); brmax = max(brmax, ra); bcmin = min(bcmin, ca); bcmax = max(bcmax, ca);
                     }
                 }
@@ -325,41 +399,52 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels) {
                     atomicMin(&S.box[g][buf][2], bcmin); atomicMax(&S.box[g][buf][3], bcmax);
                 }
             }
-            uint32_t vmax;
-            if (k1_max) {
-                vmax = (vmaxd == vmaxd) ? (uint32_t)vmaxd : 0u;      // NaN: empty mask, no pair exists anyway
-            } else {
+            uint32_t mul = I.mul, sh = I.sh;
+            bool fast = I.fast != 0u;
+            if (!k1_max) {
                 const uint32_t wm = __reduce_max_sync(0xffffffffu, max(mx2 & 0xffffu, mx2 >> 16));
                 if (lane == 0) S.wmax[g][gw] = wm;
                 bar_sync(id_sync, gthreads);
-                vmax = lane < gthreads / 32 ? S.wmax[g][lane] : 0u;
+                uint32_t vmax = lane < gthreads / 32 ? S.wmax[g][lane] : 0u;
                 vmax = __reduce_max_sync(0xffffffffu, vmax);
+                uint32_t f = 0u;
+                if (lane == 0) { f = k3_magic_fast(vmax, mul) ? 1u : 0u; if (!f) k3_magic(vmax, mul, sh); }
+                mul = __shfl_sync(0xffffffffu, mul, 0);
+                sh = __shfl_sync(0xffffffffu, sh, 0);
+                fast = __shfl_sync(0xffffffffu, f, 0) != 0u;
             }
 
-            // ---- 2. quantise to 8 bits into shared memory ----
-            uint32_t mul = 0, sh = 24;
-            if (lane == 0) k3_magic(vmax, mul, sh);
-            mul = __shfl_sync(0xffffffffu, mul, 0);
-            sh = __shfl_sync(0xffffffffu, sh, 0);
-            for (int idx = gt; idx < nfull; idx += gthreads) {
-                const uint4 v = ld_reuse(px4 + idx);
-                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-                uint32_t q[2] = {0u, 0u};
+            // ---- 2. quantise to 8 bits into shared memory (out-of-mask pixels may exceed the maximum: their
+            //         bytes are never part of a pair, only the low byte is kept) ----
+            if (fast) {
+                for (int idx = gt; idx < nfull; idx += gthreads) {
+                    const uint4 v = px4[idx];
+                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t q[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // pixels outside the mask may exceed vmax; they never enter a pair, clamp them
-                    uint32_t a = k3_quant(w4[k] & 0xffffu, mul, sh), b = k3_quant(w4[k] >> 16, mul, sh);
-                    if (MASKED) { a = min(a, 255u); b = min(b, 255u); }
-                    q[k >> 1] |= (a | (b << 8)) << (16 * (k & 1));
+                    for (int k = 0; k < 4; ++k)
+                        q[k] = __byte_perm(__umulhi(w4[k] & 0xffffu, mul), __umulhi(w4[k] >> 16, mul), 0x0040);
+                    *reinterpret_cast<uint2*>(Gp.q8 + 2 * idx) = make_uint2(__byte_perm(q[0], q[1], 0x5410), __byte_perm(q[2], q[3], 0x5410));
                 }
-                *reinterpret_cast<uint2*>(Gp.q8 + 2 * idx) = make_uint2(q[0], q[1]);
+            } else {
+                for (int idx = gt; idx < nfull; idx += gthreads) {
+                    const uint4 v = px4[idx];
+                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t q[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        q[k] = __byte_perm(k3_quant(w4[k] & 0xffffu, mul, sh), k3_quant(w4[k] >> 16, mul, sh), 0x0040);
+                    *reinterpret_cast<uint2*>(Gp.q8 + 2 * idx) = make_uint2(__byte_perm(q[0], q[1], 0x5410), __byte_perm(q[2], q[3], 0x5410));
+                }
             }
             if (gt < rem) {
                 const int i = nfull * 8 + gt;
-                reinterpret_cast<uint8_t*>(Gp.q8)[i] = (uint8_t)min(k3_quant(T.px[i], mul, sh), 255u);
+                const uint32_t qv = fast ? __umulhi((uint32_t)pxs[i], mul) : k3_quant(pxs[i], mul, sh);
+                reinterpret_cast<uint8_t*>(Gp.q8)[i] = (uint8_t)qv;
             }
         }
         bar_sync(id_sync, gthreads);                       // this tile staged
+        if (gw == 0 && j + 1 < my_count) announce(t + t_step, buf ^ 1);   // the raw buffer is free again
         // box of pixels that can take part in a pair: the tile, or the mask's bounding box
         int bx[4] = {0, th - 1, 0, tw - 1};
         if (MASKED && active) { bx[0] = S.box[g][buf][0]; bx[1] = S.box[g][buf][1]; bx[2] = S.box[g][buf][2]; bx[3] = S.box[g][buf][3]; }
@@ -397,7 +482,8 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels) {
                     atomicAdd(&Acc.s[0], r0); atomicAdd(&Acc.s[1], r1); atomicAdd(&Acc.s[2], r2); atomicAdd(&Acc.s[3], r3);
                     atomicAdd(&Acc.s[4], r4); atomicAdd(&Acc.s[5], r5); atomicAdd(&Acc.s[7], r7);
                     atomicAdd(&Acc.np, r8);
-                    atomicAdd(&Acc.hom, hf);
+                    const uint32_t lo = (uint32_t)hf, old = atomicAdd(&Acc.hom_lo, lo);
+                    atomicAdd(&Acc.hom_hi, (uint32_t)(hf >> 32) + (old + lo < old ? 1u : 0u));
                 }
                 A = K3Acc{0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0};
                 np = 0u;
@@ -461,15 +547,19 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels) {
             const uint32_t so = __reduce_add_sync(0xffffffffu, sold);
             if (lane == 0 && so) atomicAdd(&Acc.s[6], so);
         }
-        bar_sync(id_sync, gthreads);                       // sums final, staging buffers free
+        if (gw == 0 && j + 1 < my_count) {
+            cp_async_wait_all();
+            if (lane == 0) publish(buf ^ 1);
+        }
+        bar_sync(id_sync, gthreads);                       // sums final, staging buffers free, next tile announced
         if (active && gw < P.n_angles && lane == 0) {
-            const uint32_t row = t / (uint32_t)P.c_out;
+            const uint32_t row = S.info[g][buf].row;
             k3_epilogue(P, P.out + (long long)row * P.row_stride, P.status ? P.status + row : nullptr,
-                        (int)(t - row * (uint32_t)P.c_out), gw, S.acc[g][buf][gw]);
+                        (int)S.info[g][buf].slot, gw, S.acc[g][buf][gw]);
             K3AccS& Acc = S.acc[g][buf][gw];
 #pragma unroll
             for (int k = 0; k < 8; ++k) Acc.s[k] = 0u;
-            Acc.hom = 0ull;
+            Acc.hom_lo = 0u; Acc.hom_hi = 0u;
             Acc.np = 0u;
         }
         if (MASKED && active && gt == 0) {

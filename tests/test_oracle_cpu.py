@@ -132,3 +132,16 @@ def test_quantiser_multiply_shift_is_exact():
         q = (x * np.uint64(255) * np.uint64(mul)) >> np.uint64(sh)
         ref = ((x.astype(np.float64) / float(vmax)) * 255).astype(np.uint8)
         assert (q == ref).all(), vmax
+
+
+def test_quantiser_single_multiply_is_exact():
+    """k3_magic_fast (csrc/k3_glcm.cuh): for 256 < max <= 4103 the quantiser is one multiply-high,
+    umulhi(x, 255 * (floor((2^32 - 1) / max) + 1)); checked against the notebook's float64 expression
+    (NB:294-295) for every x <= max and every maximum of the range."""
+    for vmax in range(257, 4104):
+        mul = 255 * (0xFFFFFFFF // vmax + 1)
+        assert mul < 2 ** 32
+        x = np.arange(0, vmax + 1, dtype=np.uint64)
+        q = (x * np.uint64(mul)) >> np.uint64(32)
+        ref = ((x.astype(np.float64) / float(vmax)) * 255).astype(np.uint8)
+        assert (q == ref).all(), vmax
