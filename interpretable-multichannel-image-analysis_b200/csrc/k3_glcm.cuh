@@ -127,13 +127,17 @@ __device__ __forceinline__ uint32_t k3_bits16(const uint32_t* b, int off) {
 }
 
 // An item is a run of up to 16 horizontally consecutive pairs (4 groups of 4) of one row: the words
-// of both pixel runs are loaded once and funnel-shifted into place.
+// of both pixel runs are loaded once and funnel-shifted into place.  When the row length is a
+// multiple of 16 the runs of one side (I for dc >= 0, J for dc < 0) are made to start at multiples
+// of 16 bytes: that side is one conflict-free 128-bit load, the other side two.
 struct K3Geom {
     int nrows, r0, c0, c1, ipr, items, w, doff;
     float rcp;                                     // 1 / ipr: row = floor((item + 0.5) * rcp), exact for item < 2^20
+    int aligned, base_j, ws, sb;                   // aligned path: which side is 16-byte aligned; word / bit shift of the other
 };
 // Pairs (r, c) -> (r + dr, c + dc) with both pixels inside the box rows [br0, br1], columns
 // [bc0, bc1] (the whole tile, or the bounding box of the mask: pairs outside it cannot exist).
+template <bool MASKED>
 __device__ __forceinline__ K3Geom k3_geom(int w, int dr, int dc, int br0, int br1, int bc0, int bc1) {
     K3Geom G;
     G.r0 = br0;
@@ -142,11 +146,27 @@ __device__ __forceinline__ K3Geom k3_geom(int w, int dr, int dc, int br0, int br
     G.c1 = bc1 + 1 - (dc > 0 ? dc : 0);
     G.w = w;
     G.doff = dr * w + dc;
+    G.aligned = 0; G.base_j = dc < 0; G.ws = 0; G.sb = 0;
     if (G.nrows <= 0 || G.c1 <= G.c0) { G.items = 0; G.ipr = 1; G.rcp = 1.0f; G.nrows = 0; return G; }
+    // unmasked tiles only: the aligned side starts at column bc0 = 0.  (Widening a mask's bounding box to the
+    // left to get there was measured slower: up to a third more items.)
+    if (!MASKED && (w & 15) == 0 && (bc0 & 15) == 0) {
+        G.aligned = 1;
+        const int other = (G.base_j ? -G.doff : G.doff) & 15;      // offset of the other side modulo 16 bytes
+        G.ws = other >> 2;
+        G.sb = (other & 3) << 3;
+    }
     G.ipr = (G.c1 - G.c0 + 15) >> 4;               // items per row
     G.rcp = __frcp_rn((float)G.ipr);
     G.items = G.nrows * G.ipr;
     return G;
+}
+
+template <int WS>
+__device__ __forceinline__ void k3_shift4(const uint4& a, const uint4& b, uint32_t sb, uint32_t (&out)[4]) {
+    const uint32_t W[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = __funnelshift_r(W[WS + k], W[WS + k + 1], sb);
 }
 
 // Load one item: the quantised bytes of both pixels of its 16 pairs (I4[k], J4[k]: pairs 4k..4k+3;
@@ -160,6 +180,26 @@ __device__ __forceinline__ bool k3_item16(const K3Group& Gp, const K3Geom& G, in
     const int nv = min(16, G.c1 - c);
     const int oi = (G.r0 + r) * G.w + c, oj = oi + G.doff;
     pm = 0xffffu >> (16 - nv);
+    if (!MASKED && G.aligned) {
+        const int ob = G.base_j ? oj : oi, oo = G.base_j ? oi : oj;      // ob is a multiple of 16
+        if (MASKED) {
+            pm &= (uint32_t)reinterpret_cast<const uint16_t*>(Gp.mbits)[ob >> 4] & k3_bits16(Gp.mbits, oo);
+            if (pm == 0u) return false;
+        }
+        const uint4 vb = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(Gp.q8) + ob);
+        const uint4* po = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(Gp.q8) + (oo & ~15));
+        const uint4 v0 = po[0], v1 = po[1];
+        uint32_t B[4] = {vb.x, vb.y, vb.z, vb.w}, O[4];
+        switch (G.ws) {
+            case 0: k3_shift4<0>(v0, v1, (uint32_t)G.sb, O); break;
+            case 1: k3_shift4<1>(v0, v1, (uint32_t)G.sb, O); break;
+            case 2: k3_shift4<2>(v0, v1, (uint32_t)G.sb, O); break;
+            default: k3_shift4<3>(v0, v1, (uint32_t)G.sb, O); break;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { I4[k] = G.base_j ? O[k] : B[k]; J4[k] = G.base_j ? B[k] : O[k]; }
+        return true;
+    }
     if (MASKED) {
         pm &= k3_bits16(Gp.mbits, oi) & k3_bits16(Gp.mbits, oj);
         if (pm == 0u) return false;
@@ -453,7 +493,7 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
         for (int a = 0; a < kMaxAngles; ++a) {
             if (a >= P.n_angles) break;
             // ---- off the table: this direction's first items become hits in registers ----
-            const K3Geom G = k3_geom(tw, P.dr[a], P.dc[a], bx[0], bx[1], bx[2], bx[3]);
+            const K3Geom G = k3_geom<MASKED>(tw, P.dr[a], P.dc[a], bx[0], bx[1], bx[2], bx[3]);
             uint32_t hit[kCache][16];
             uint32_t sold = 0u, valid = 0u, np = 0u;
             K3Acc A = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0};
