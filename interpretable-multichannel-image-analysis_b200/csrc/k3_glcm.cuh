@@ -391,6 +391,7 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
             // ---- 1. tile maximum (over the mask when masked); stage the mask bits and their bounding box ----
             uint32_t mx2 = 0u;
             int brmin = 1 << 30, brmax = -1, bcmin = 1 << 30, bcmax = -1;
+            const float rtw = __frcp_rn((float)tw);
             for (int idx = gt; idx < nfull && (MASKED || !k1_max); idx += gthreads) {
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
                 if (!k1_max) v = px4[idx];
@@ -403,7 +404,7 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
                     const uint32_t bits8 = (b0 & 0xfu) | ((b1 & 0xfu) << 4);
                     mbytes[idx] = (uint8_t)bits8;
                     if (bits8) {
-                        const int p0 = 8 * idx, ra = p0 / tw, ca = p0 - ra * tw;
+                        const int p0 = 8 * idx, ra = (int)(((float)p0 + 0.5f) * rtw), ca = p0 - ra * tw;   // exact: p0 < 2^20
                         if (ca + 7 < tw) {                 // the 8 pixels lie in one row
                             brmin = min(brmin, ra); brmax = max(brmax, ra);
                             bcmin = min(bcmin, ca + __ffs(bits8) - 1); bcmax = max(bcmax, ca + 31 - __clz(bits8));
