@@ -390,51 +390,129 @@ __global__ void __launch_bounds__(32, 20) k4w_shape_kernel(const __grid_constant
         uint32_t area = 0, sr = 0, sc = 0, srr = 0, scc = 0, src = 0;
         unsigned long long mq[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // M00 M10 M01 M20 M11 M02 M30 M21 M12 M03
 
-        // ---- pass A: lanes over columns, rows in sequence (four rows of loads in flight) ----
-        for (int c0 = 0; c0 < w; c0 += 32) {
-            const int c = c0 + lane;
-            const bool inb = c < w;
-            uint32_t cnt = 0, csr = 0, csrr = 0, b0 = 0, b1 = 0;
-            unsigned long long b2 = 0, b3 = 0;
-            const uint8_t* mp = T.mk + (inb ? c : 0);
-            const uint16_t* pp = T.px + (inb ? c : 0);
-            uint32_t* mr = mrow + (c0 >> 5);
-            auto row = [&](int r, bool m, uint32_t pxv) {
-                const uint32_t bal = __ballot_sync(0xffffffffu, m);
-                if (lane == 0) mr[r * Pw] = bal;
-                const uint32_t m1 = m ? 1u : 0u, im = m ? pxv : 0u;
-                const uint32_t r1 = r, r2 = r * r, r3 = r2 * r;
-                cnt += m1; csr += m1 * r1; csrr += m1 * r2;
-                rmin = m ? min(rmin, r) : rmin; rmax = m ? max(rmax, r) : rmax;
-                b0 += im; b1 += im * r1;
-                b2 += (unsigned long long)im * r2;
-                b3 += (unsigned long long)im * r3;
+        // ---- pass A ----
+        const int cpr = w >> 3;                            // 8-pixel chunks per row
+        if ((w & 7) == 0 && (cpr & (cpr - 1)) == 0 && cpr <= 32) {
+            // Vector pass (w = 8, 16, .. 256): chunks of 8 consecutive pixels lane-strided over the tile, one
+            // 128-bit pixel load + one 64-bit mask load each.  32 is a multiple of cpr, so a lane keeps its
+            // column c0 and walks down the rows: per chunk only the local sums sum_k k^q I_k (IDP.2A with
+            // constant weights) and sum_k k^q m_k (IDP.4A) times r^p are accumulated; the column index is
+            // folded in once per tile.
+            const int lg = 31 - __clz(cpr), lc = lane & (cpr - 1), c0 = lc << 3;
+            const int rstep = 32 >> lg, nchunk = h << lg;
+            if (w & 31) {                                  // bytes behind the row end inside the last word
+                for (int k = lane; k < h * Pw; k += 32) mrow[k] = 0u;
+                __syncwarp();
+            }
+            uint8_t* mbytes = reinterpret_cast<uint8_t*>(mrow) + lc;
+            const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
+            const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
+            uint32_t cntL = 0, skL = 0, sk2L = 0, rc1 = 0, rc2 = 0, rsk = 0, colbits = 0;
+            uint32_t B00 = 0, B01 = 0, B02 = 0, B03 = 0;
+            unsigned long long B10 = 0, B20 = 0, B30 = 0, B11 = 0, B21 = 0, B12 = 0;
+            auto chunk = [&](int r, uint4 v, uint2 m) {
+                uint32_t bits8 = 0xffu, b03 = 0x01010101u, b47 = 0x01010101u;
+                if (MASKED) {
+                    const uint32_t n0 = __vcmpne4(m.x, 0u), n1 = __vcmpne4(m.y, 0u);
+                    b03 = n0 & 0x01010101u; b47 = n1 & 0x01010101u;
+                    bits8 = (((b03 * 0x01020408u) >> 24) & 0xfu) | (((b47 * 0x01020408u) >> 20) & 0xf0u);
+                    v.x &= __byte_perm(n0, 0u, 0x1100); v.y &= __byte_perm(n0, 0u, 0x3322);
+                    v.z &= __byte_perm(n1, 0u, 0x1100); v.w &= __byte_perm(n1, 0u, 0x3322);
+                }
+                mbytes[r * (Pw << 2)] = (uint8_t)bits8;
+                const uint32_t cnt = __popc(bits8);
+                const uint32_t sk = __dp4a(b47, 0x07060504u, __dp4a(b03, 0x03020100u, 0u));
+                const uint32_t sk2 = __dp4a(b47, 0x31241910u, __dp4a(b03, 0x09040100u, 0u));
+                const uint32_t r1 = (uint32_t)r, r2 = r1 * r1;
+                cntL += cnt; skL += sk; sk2L += sk2; rc1 += r1 * cnt; rc2 += r2 * cnt; rsk += r1 * sk;
+                colbits |= bits8;
+                if (cnt) { rmin = min(rmin, r); rmax = r; }
+                if (want_mom) {
+                    const uint32_t s0 = __dp2a_lo(v.w, 0x0101u, __dp2a_lo(v.z, 0x0101u, __dp2a_lo(v.y, 0x0101u, __dp2a_lo(v.x, 0x0101u, 0u))));
+                    const uint32_t s1 = __dp2a_lo(v.w, 0x0706u, __dp2a_lo(v.z, 0x0504u, __dp2a_lo(v.y, 0x0302u, __dp2a_lo(v.x, 0x0100u, 0u))));
+                    const uint32_t s2 = __dp2a_lo(v.w, 0x3124u, __dp2a_lo(v.z, 0x1910u, __dp2a_lo(v.y, 0x0904u, __dp2a_lo(v.x, 0x0100u, 0u))));
+                    // cubes 0 1 8 27 64 125 216 343: 343 = 255 + 88 does not fit one byte weight
+                    const uint32_t s3 = __dp2a_lo(v.w, 0x5800u, __dp2a_lo(v.w, 0xffd8u, __dp2a_lo(v.z, 0x7d40u, __dp2a_lo(v.y, 0x1b08u, __dp2a_lo(v.x, 0x0100u, 0u)))));
+                    const uint32_t r3 = r2 * r1;
+                    B00 += s0; B01 += s1; B02 += s2; B03 += s3;
+                    B10 += (unsigned long long)s0 * r1; B20 += (unsigned long long)s0 * r2; B30 += (unsigned long long)s0 * r3;
+                    B11 += (unsigned long long)s1 * r1; B21 += (unsigned long long)s1 * r2;
+                    B12 += (unsigned long long)s2 * r1;
+                }
             };
-            int r = 0;
-            for (; r + 4 <= h; r += 4) {
-                bool m[4];
-                uint32_t pxv[4];
+            int idx = lane, r = lane >> lg;
+            for (; idx + 96 < nchunk; idx += 128, r += 4 * rstep) {      // four chunks of loads in flight
+                uint4 v[4];
+                uint2 m[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    m[u] = inb && (!MASKED || mp[(r + u) * w] != 0);
-                    pxv[u] = (want_mom && inb) ? (uint32_t)pp[(r + u) * w] : 0u;
+                    v[u] = want_mom ? ld_stream(px4 + idx + 32 * u) : make_uint4(0u, 0u, 0u, 0u);
+                    m[u] = MASKED ? __ldg(mk2 + idx + 32 * u) : make_uint2(0u, 0u);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) row(r + u, m[u], pxv[u]);
+                for (int u = 0; u < 4; ++u) chunk(r + u * rstep, v[u], m[u]);
             }
-            for (; r < h; ++r) {
-                const bool m = inb && (!MASKED || mp[r * w] != 0);
-                row(r, m, (want_mom && inb) ? (uint32_t)pp[r * w] : 0u);
-            }
-            if (cnt) { cmin = min(cmin, c); cmax = max(cmax, c); }
-            const uint32_t c1 = inb ? c : 0, c2 = c1 * c1, c3 = c2 * c1;
-            area += cnt; sr += csr; srr += csrr; sc += c1 * cnt; scc += c2 * cnt; src += c1 * csr;
+            for (; idx < nchunk; idx += 32, r += rstep)
+                chunk(r, want_mom ? ld_stream(px4 + idx) : make_uint4(0u, 0u, 0u, 0u), MASKED ? __ldg(mk2 + idx) : make_uint2(0u, 0u));
+            // fold the lane's column in: c = c0 + k
+            const uint32_t c1 = (uint32_t)c0, c2 = c1 * c1;
+            area = cntL; sr = rc1; srr = rc2;
+            sc = c1 * cntL + skL; scc = c2 * cntL + 2u * c1 * skL + sk2L; src = c1 * rc1 + rsk;
+            if (colbits) { cmin = c0 + __ffs(colbits) - 1; cmax = c0 + 31 - __clz(colbits); }
             if (want_mom) {
-                mq[0] += b0; mq[1] += b1; mq[3] += b2; mq[6] += b3;
-                mq[2] += (unsigned long long)b0 * c1; mq[4] += (unsigned long long)b1 * c1;
-                mq[7] += b2 * c1;
-                mq[5] += (unsigned long long)b0 * c2; mq[8] += (unsigned long long)b1 * c2;
-                mq[9] += (unsigned long long)b0 * c3;
+                const unsigned long long C1 = c1, C2 = c2, C3 = (unsigned long long)c2 * c1;
+                mq[0] = B00; mq[1] = B10; mq[3] = B20; mq[6] = B30;
+                mq[2] = C1 * B00 + B01; mq[4] = C1 * B10 + B11; mq[7] = C1 * B20 + B21;
+                mq[5] = C2 * B00 + 2ull * C1 * B01 + B02; mq[8] = C2 * B10 + 2ull * C1 * B11 + B12;
+                mq[9] = C3 * B00 + 3ull * C2 * B01 + 3ull * C1 * B02 + B03;
+            }
+        } else {
+            // ---- pass A: lanes over columns, rows in sequence (four rows of loads in flight) ----
+            for (int c0 = 0; c0 < w; c0 += 32) {
+                const int c = c0 + lane;
+                const bool inb = c < w;
+                uint32_t cnt = 0, csr = 0, csrr = 0, b0 = 0, b1 = 0;
+                unsigned long long b2 = 0, b3 = 0;
+                const uint8_t* mp = T.mk + (inb ? c : 0);
+                const uint16_t* pp = T.px + (inb ? c : 0);
+                uint32_t* mr = mrow + (c0 >> 5);
+                auto row = [&](int r, bool m, uint32_t pxv) {
+                    const uint32_t bal = __ballot_sync(0xffffffffu, m);
+                    if (lane == 0) mr[r * Pw] = bal;
+                    const uint32_t m1 = m ? 1u : 0u, im = m ? pxv : 0u;
+                    const uint32_t r1 = r, r2 = r * r, r3 = r2 * r;
+                    cnt += m1; csr += m1 * r1; csrr += m1 * r2;
+                    rmin = m ? min(rmin, r) : rmin; rmax = m ? max(rmax, r) : rmax;
+                    b0 += im; b1 += im * r1;
+                    b2 += (unsigned long long)im * r2;
+                    b3 += (unsigned long long)im * r3;
+                };
+                int r = 0;
+                for (; r + 4 <= h; r += 4) {
+                    bool m[4];
+                    uint32_t pxv[4];
+    #pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        m[u] = inb && (!MASKED || mp[(r + u) * w] != 0);
+                        pxv[u] = (want_mom && inb) ? (uint32_t)pp[(r + u) * w] : 0u;
+                    }
+    #pragma unroll
+                    for (int u = 0; u < 4; ++u) row(r + u, m[u], pxv[u]);
+                }
+                for (; r < h; ++r) {
+                    const bool m = inb && (!MASKED || mp[r * w] != 0);
+                    row(r, m, (want_mom && inb) ? (uint32_t)pp[r * w] : 0u);
+                }
+                if (cnt) { cmin = min(cmin, c); cmax = max(cmax, c); }
+                const uint32_t c1 = inb ? c : 0, c2 = c1 * c1, c3 = c2 * c1;
+                area += cnt; sr += csr; srr += csrr; sc += c1 * cnt; scc += c2 * cnt; src += c1 * csr;
+                if (want_mom) {
+                    mq[0] += b0; mq[1] += b1; mq[3] += b2; mq[6] += b3;
+                    mq[2] += (unsigned long long)b0 * c1; mq[4] += (unsigned long long)b1 * c1;
+                    mq[7] += b2 * c1;
+                    mq[5] += (unsigned long long)b0 * c2; mq[8] += (unsigned long long)b1 * c2;
+                    mq[9] += (unsigned long long)b0 * c3;
+                }
             }
         }
         __syncwarp();
