@@ -45,7 +45,7 @@ def test_reference_shaped_functions(golden, torch_mod):
 
 
 @pytest.mark.parametrize("shape", [(64, 64), (37, 91), (128, 128), (9, 5), (7, 6), (1, 1), (33, 17),
-                                   (3, 300), (181, 181), (2, 16384)])
+                                   (3, 300), (181, 181), (2, 16384), (20, 8), (50, 16), (41, 32), (30, 256)])
 def test_distributions_all_blocks(shape, torch_mod):
     h, w = shape
     rng = np.random.default_rng(h * 1000 + w)
@@ -97,7 +97,7 @@ def test_glcm_bins_bit_exact(torch_mod):
             assert (counts[0, c] == want).all(), ("masked", h, w, k)
 
 
-@pytest.mark.parametrize("shape", [(64, 64), (37, 91), (128, 128), (20, 9)])
+@pytest.mark.parametrize("shape", [(64, 64), (37, 91), (128, 128), (20, 9), (20, 8), (50, 16), (41, 32), (30, 256)])
 def test_masked_all_blocks(shape, torch_mod):
     h, w = shape
     rng = np.random.default_rng(77 + h)
