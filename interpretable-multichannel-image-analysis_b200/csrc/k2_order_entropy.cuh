@@ -395,19 +395,22 @@ struct K2cSmem {
     unsigned long long wacc[kK2cWarps];
 };
 
+// One pixel into the warp's histogram.  inb = all ones when the pixel counts (inside the mask), else 0:
+// then the increment is 0 and the selected old count is 0 (G[0] = 0), so the masked path needs no
+// branch and no dummy word.  The 16-bit half of the returned word is picked
+// by IDP.2A with a one-hot byte pair.
 template <bool MASKED>
-__device__ __forceinline__ void k2c_px(K2cSmem& S, const Params& P, uint32_t x, bool in, uint32_t vmin,
-                                       uint32_t& cnt, uint32_t& maxold, unsigned long long& acc) {
+__device__ __forceinline__ void k2c_px(K2cSmem& S, const Params& P, uint32_t x, uint32_t inb, uint32_t vmin,
+                                       uint32_t& maxold, unsigned long long& acc) {
     const uint32_t bin = x - vmin;
+    const uint32_t p = bin & 1u;
     uint32_t off = (bin << 1) & (uint32_t)(kK2cWords * 4 - 4);
-    uint32_t sh = (bin & 1u) << 4;
-    if (MASKED) {                                        // branch-free: outside the mask -> this lane's dummy word
-        off = in ? off : (uint32_t)(kK2cWords * 4) + 4u * (threadIdx.x & 31);
-        sh = in ? sh : 0u;
-    }
+    uint32_t sel = p * 0xffu + 1u, inc = p * 0xffffu + 1u;
+    // outside the mask: add 0 to word `lane` (distinct banks; equal background values would otherwise
+    // serialise on one address)
+    if (MASKED) { sel &= inb; inc &= inb; off = (off & inb) | (4u * (threadIdx.x & 31) & ~inb); }
     uint32_t* word = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(S.hist) + off);
-    uint32_t old = (atomicAdd(word, 1u << sh) >> sh) & 0xffffu;
-    if (MASKED) { old = in ? old : 0u; cnt += in ? 1u : 0u; }
+    const uint32_t old = __dp2a_lo(atomicAdd(word, inc), sel, 0u);
     acc += __ldg(P.gfix + old);
     maxold = max(maxold, old);
 }
@@ -455,19 +458,20 @@ __global__ void __launch_bounds__(kK2cThreads, 24) k2c_order_entropy_kernel(cons
             uint2 m = make_uint2(0u, 0u);
             if (MASKED) m = __ldg(mk2 + idx);
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t nz[2] = {__vcmpne4(m.x, 0u), __vcmpne4(m.y, 0u)};      // 0xff per pixel inside the mask
+            if (MASKED) cnt += (__popc(nz[0]) + __popc(nz[1])) >> 3;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t mb = (k < 2 ? m.x : m.y) >> (16 * (k & 1));
-                k2c_px<MASKED>(S, P, w[k] & 0xffffu, (mb & 0xffu) != 0u, vmin, cnt, maxold, acc);
-                k2c_px<MASKED>(S, P, w[k] >> 16, (mb & 0xff00u) != 0u, vmin, cnt, maxold, acc);
+                const uint32_t n4 = nz[k >> 1];
+                k2c_px<MASKED>(S, P, w[k] & 0xffffu, __byte_perm(n4, 0u, (k & 1) ? 0x2222 : 0x0000), vmin, maxold, acc);
+                k2c_px<MASKED>(S, P, w[k] >> 16, __byte_perm(n4, 0u, (k & 1) ? 0x3333 : 0x1111), vmin, maxold, acc);
             }
         }
         if (tid < rem) {
             const int i = nfull * 8 + tid;
             const bool in = !MASKED || T.mk[i] != 0;
             if (in) {
-                uint32_t c1 = 0;
-                k2c_px<false>(S, P, T.px[i], true, vmin, c1, maxold, acc);
+                k2c_px<false>(S, P, T.px[i], 0xffffffffu, vmin, maxold, acc);
                 cnt += 1;
             }
         }
