@@ -395,24 +395,17 @@ struct K2cSmem {
     unsigned long long wacc[kK2cWarps];
 };
 
-// One pixel into the warp's histogram.  inb = all ones when the pixel counts (inside the mask), else 0:
-// then the increment is 0 and the selected old count is 0 (G[0] = 0), so the masked path needs no
-// branch and no dummy word.  The 16-bit half of the returned word is picked
-// by IDP.2A with a one-hot byte pair.
+// One pixel into the warp's histogram (fire-and-forget: the counts are read back once, by the pass that
+// also clears them).  inb = all ones when the pixel counts (inside the mask), else 0: then the increment
+// is 0, on word `lane` (distinct banks; equal background values would otherwise serialise on one address),
+// so the masked path needs no branch and no dummy word.
 template <bool MASKED>
-__device__ __forceinline__ void k2c_px(K2cSmem& S, const Params& P, uint32_t x, uint32_t inb, uint32_t vmin,
-                                       uint32_t& maxold, unsigned long long& acc) {
+__device__ __forceinline__ void k2c_px(K2cSmem& S, uint32_t x, uint32_t inb, uint32_t vmin) {
     const uint32_t bin = x - vmin;
-    const uint32_t p = bin & 1u;
     uint32_t off = (bin << 1) & (uint32_t)(kK2cWords * 4 - 4);
-    uint32_t sel = p * 0xffu + 1u, inc = p * 0xffffu + 1u;
-    // outside the mask: add 0 to word `lane` (distinct banks; equal background values would otherwise
-    // serialise on one address)
-    if (MASKED) { sel &= inb; inc &= inb; off = (off & inb) | (4u * (threadIdx.x & 31) & ~inb); }
-    uint32_t* word = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(S.hist) + off);
-    const uint32_t old = __dp2a_lo(atomicAdd(word, inc), sel, 0u);
-    acc += __ldg(P.gfix + old);
-    maxold = max(maxold, old);
+    uint32_t inc = (bin & 1u) * 0xffffu + 1u;
+    if (MASKED) { inc &= inb; off = (off & inb) | (4u * (threadIdx.x & 31) & ~inb); }
+    atomicAdd(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(S.hist) + off), inc);
 }
 
 template <bool MASKED>
@@ -451,27 +444,33 @@ __global__ void __launch_bounds__(kK2cThreads, 24) k2c_order_entropy_kernel(cons
         const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
         const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
         const int nfull = T.n >> 3, rem = T.n & 7;
-        uint32_t cnt = 0, maxold = 0;
-        unsigned long long acc = 0ull;
+        uint32_t cnt = 0;
+        // software pipeline: the next chunk's loads are in flight while this one goes into the histogram
+        uint4 vn = make_uint4(0u, 0u, 0u, 0u);
+        uint2 mn = make_uint2(0u, 0u);
+        if (tid < nfull) { vn = ld_stream(px4 + tid); if (MASKED) mn = __ldg(mk2 + tid); }
         for (int idx = tid; idx < nfull; idx += kK2cThreads) {
-            const uint4 v = ld_stream(px4 + idx);
-            uint2 m = make_uint2(0u, 0u);
-            if (MASKED) m = __ldg(mk2 + idx);
+            const uint4 v = vn;
+            const uint2 m = mn;
+            if (idx + kK2cThreads < nfull) {
+                vn = ld_stream(px4 + idx + kK2cThreads);
+                if (MASKED) mn = __ldg(mk2 + idx + kK2cThreads);
+            }
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
             const uint32_t nz[2] = {__vcmpne4(m.x, 0u), __vcmpne4(m.y, 0u)};      // 0xff per pixel inside the mask
             if (MASKED) cnt += (__popc(nz[0]) + __popc(nz[1])) >> 3;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t n4 = nz[k >> 1];
-                k2c_px<MASKED>(S, P, w[k] & 0xffffu, __byte_perm(n4, 0u, (k & 1) ? 0x2222 : 0x0000), vmin, maxold, acc);
-                k2c_px<MASKED>(S, P, w[k] >> 16, __byte_perm(n4, 0u, (k & 1) ? 0x3333 : 0x1111), vmin, maxold, acc);
+                k2c_px<MASKED>(S, w[k] & 0xffffu, __byte_perm(n4, 0u, (k & 1) ? 0x2222 : 0x0000), vmin);
+                k2c_px<MASKED>(S, w[k] >> 16, __byte_perm(n4, 0u, (k & 1) ? 0x3333 : 0x1111), vmin);
             }
         }
         if (tid < rem) {
             const int i = nfull * 8 + tid;
             const bool in = !MASKED || T.mk[i] != 0;
             if (in) {
-                k2c_px<false>(S, P, T.px[i], 0xffffffffu, vmin, maxold, acc);
+                k2c_px<false>(S, T.px[i], 0xffffffffu, vmin);
                 cnt += 1;
             }
         }
@@ -521,27 +520,32 @@ __global__ void __launch_bounds__(kK2cThreads, 24) k2c_order_entropy_kernel(cons
                                          : __dadd_rn((double)a, __dmul_rn(diff, g));
             }
         }
-        if (n > 0 && (int)maxold + 1 == n) S.constant = 1;   // one value only: entropy is exactly 0
-        acc = warp_sum_redux(acc);
-        if (lane == 0) S.wacc[warp] = acc;
-        __syncthreads();                                     // walk done; n read; partial sums visible
+        __syncthreads();                                     // walk done; n read
+        // entropy = log2 n - (1/n) sum_bins c log2 c, in the pass that clears the used range: fixed order
+        // per lane and a fixed shuffle tree, so the double sum is reproducible bit for bit
         const int used_words = (int)(range >> 1) + 1;
-        for (int k = tid; k < used_words; k += kK2cThreads) S.hist[k] = 0u;
-        if (MASKED && tid < 32) S.dummy[tid] = 0u;
+        double hs = 0.0;
+        for (int k = tid; k < used_words; k += kK2cThreads) {
+            const uint32_t wv = S.hist[k];
+            if (wv) {
+                const uint32_t c0 = wv & 0xffffu, c1 = wv >> 16;
+                hs = fma((double)c0, __ldg(P.log2tab + c0), hs);       // log2tab[0] = 0
+                hs = fma((double)c1, __ldg(P.log2tab + c1), hs);
+                S.hist[k] = 0u;
+            }
+        }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) hs += __shfl_xor_sync(0xffffffffu, hs, o2);
         if (tid == 0) {
             if (n > 0) {
-                unsigned long long tot = 0ull;
-#pragma unroll
-                for (int w = 0; w < kK2cWarps; ++w) tot += S.wacc[w];
-                const double H = __ldg(P.log2tab + n) - ((double)tot * 2.2737367544323206e-13) / (double)n;
-                o[16] = S.constant ? 0.0 : H;
+                const double H = __ldg(P.log2tab + n) - hs / (double)n;
+                o[16] = range == 0u ? 0.0 : H;               // one value only: entropy is exactly 0
             } else {
                 const double nan = qnan();
 #pragma unroll
                 for (int q = 1; q <= 9; ++q) o[q] = nan;
                 o[16] = nan;
             }
-            S.constant = 0;
             S.cnt = 0u;
         }
         __syncthreads();                                     // table clean, scratch consumed
