@@ -37,7 +37,7 @@ __host__ __device__ inline size_t k3_group_bytes(int max_pixels, bool masked) {
 }
 // prefetch buffer of a group: the next tile's raw pixels, then its mask bytes (max_pixels is a multiple of 8)
 __host__ __device__ inline size_t k3_raw_bytes(int max_pixels, bool masked) {
-    return (size_t)max_pixels * 2 + (masked ? (size_t)max_pixels : 0);
+    return ((size_t)max_pixels * 2 + (masked ? (size_t)max_pixels : 0) + 15) & ~(size_t)15;
 }
 
 // What the first warp of a group announces about the group's next tile while the current one is under way.
@@ -52,7 +52,7 @@ struct K3AccS {
     uint32_t hom_lo, hom_hi;         // sum of 1 / (1 + d^2) in 2^-40 fixed point (64-bit shared atomics are CAS loops)
     uint32_t np, pad;                // pairs walked (16 per item), existing or not
 };
-struct K3Smem {
+struct alignas(16) K3Smem {                    // the staging buffers behind it hold 16-byte vectors
     uint32_t hist[32768];
     double homtab[256];                         // 1 / (1 + d^2)
     K3AccS acc[4][2][kMaxAngles];               // per group, tile parity (the epilogue of a tile overlaps the

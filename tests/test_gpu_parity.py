@@ -144,6 +144,22 @@ def test_variable_sizes(torch_mod):
         compare_tables(gotm[i:i + 1], want, cols, label="var masked %d %s" % (i, o.shape))
 
 
+def test_odd_size_batch_uses_every_group(torch_mod):
+    """More tiles than SMs with a slot size that is not a multiple of 16 pixels: every thread group of the
+    GLCM kernel stages tiles, so the per-group prefetch buffers must stay 16-byte aligned."""
+    rng = np.random.default_rng(17)
+    n, h, w, c = 64, 37, 91, 5
+    img = rng.integers(0, 3000, (n, h, w, c)).astype(np.uint16)
+    mask = (rng.random((n, h, w, c)) < 0.7).astype(np.uint8)
+    cols = imf.feature_columns(c, n_angles=4, shape=True, moments=True)
+    got = imf.extract_features(img, mask, four_directions=True, shape=True, moments=True)
+    want = c_oracle.table(_planar(img), _planar(mask), glcm=True, n_angles=4, shape=True, moments=True)
+    compare_tables(got, want, cols, label="odd batch masked")
+    got = imf.extract_features(img, four_directions=True, shape=True, moments=True)
+    want = c_oracle.table(_planar(img), glcm=True, n_angles=4, shape=True, moments=True)
+    compare_tables(got, want, cols, label="odd batch")
+
+
 def test_synth_device_matches_numpy_mirror(torch_mod):
     from imfeat_b200 import synth
     ex = imf.get_extractor()
