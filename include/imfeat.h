@@ -163,6 +163,22 @@ int imfeat_synth_device(imfeat_ctx *ctx, uint64_t seed, int64_t first_object,
                         int32_t *d_sizes, void *stream);
 
 /*
+ * Table post-processing on the device: the notebook's MinMaxScaler step
+ * (channel_importance_hand_crafted_features.ipynb cell 16, NB:389-394:
+ * `norm = MinMaxScaler().fit(X_train); X_train = norm.transform(X_train); X_test = norm.transform(X_test)`),
+ * sklearn semantics (nanmin / nanmax per column, ranges below 10 eps scale by 1, X * scale_ + min_).
+ *
+ * imfeat_minmax_fit_device: d_table float64[n_rows][row_stride] (first n_cols cells of a row are used);
+ * d_stats float64[4][n_cols] receives data_min_, data_max_, scale_, min_.
+ * imfeat_minmax_transform_device: d_out[r][c] = d_in[r][c] * scale_[c] + min_[c]; d_out may alias d_in.
+ */
+int imfeat_minmax_fit_device(imfeat_ctx *ctx, const double *d_table, int64_t n_rows, int32_t n_cols,
+                             int64_t row_stride, double *d_stats, void *stream);
+int imfeat_minmax_transform_device(imfeat_ctx *ctx, const double *d_in, int64_t n_rows,
+                                   int32_t n_cols, int64_t row_stride_in, const double *d_stats,
+                                   double *d_out, int64_t row_stride_out, void *stream);
+
+/*
  * Optional per-kernel device timing (CUDA events on the launching stream, resolved lazily, the
  * stream is not serialised).  imfeat_kernel_times returns, per kernel group
  * [0] K1 moments, [1] K2 order statistics + entropy, [2] K3 GLCM, [3] K4 shape/moments,

@@ -5,8 +5,9 @@ aliechoes/interpretable-multichannel-image-analysis' ``channel_importance_hand_c
 notebook (cell 13 functions + the cell 17 loop).  All arithmetic runs in hand-written sm_100a CUDA
 kernels behind the C ABI of ``include/imfeat.h``; there is no CPU fallback.
 """
-from . import ablation, batcher, distributed, schema, synth
+from . import ablation, batcher, distributed, postprocess, schema, synth
 from .batcher import PinnedBatcher
+from .postprocess import MinMaxScaler
 from ._lib import ImfeatError
 from .extractor import (FeatureExtractor, basic_statistical_features, extract_features,
                         get_extractor, glcm_features, plane_stride_for)
@@ -15,5 +16,5 @@ from .schema import feature_columns
 __all__ = [
     "FeatureExtractor", "ImfeatError", "basic_statistical_features", "extract_features",
     "feature_columns", "get_extractor", "glcm_features", "plane_stride_for", "schema",
-    "ablation", "batcher", "distributed", "synth", "PinnedBatcher",
+    "ablation", "batcher", "distributed", "postprocess", "synth", "PinnedBatcher", "MinMaxScaler",
 ]

@@ -30,6 +30,7 @@ EXPORTS = [
     "imfeat_last_error", "imfeat_row_width", "imfeat_extract_device", "imfeat_extract_host",
     "imfeat_extract_host_hwc", "imfeat_glcm_counts_device", "imfeat_pack_hwc_device",
     "imfeat_synth_device", "imfeat_launch_count", "imfeat_enable_timing", "imfeat_kernel_times",
+    "imfeat_minmax_fit_device", "imfeat_minmax_transform_device",
 ]
 
 
@@ -86,6 +87,10 @@ def load(build_if_missing=True):
     L.imfeat_enable_timing.restype = ctypes.c_int
     L.imfeat_kernel_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
     L.imfeat_kernel_times.restype = ctypes.c_int
+    L.imfeat_minmax_fit_device.argtypes = [vp, vp, i64, i32, i64, vp, vp]
+    L.imfeat_minmax_fit_device.restype = ctypes.c_int
+    L.imfeat_minmax_transform_device.argtypes = [vp, vp, i64, i32, i64, vp, vp, i64, vp]
+    L.imfeat_minmax_transform_device.restype = ctypes.c_int
     _LIB = L
     return L
 

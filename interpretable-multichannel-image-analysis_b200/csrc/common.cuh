@@ -132,18 +132,7 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Two thread groups per CTA share one 128 KB shared-memory table in turns ("ping-pong"): while one
-// group owns the table (atomics -> read -> sparse clear), the other does its table-free work
-// (loads, reductions, epilogues) for the next tile.  Barrier ids: 1+g group-internal,
-// 3+g "table is free for group g".
-constexpr int kGroupThreads = 512;
-constexpr int kGroupWarps = kGroupThreads / 32;
-constexpr int kPingPongThreads = 2 * kGroupThreads;
-__device__ __forceinline__ void group_sync(int g) { bar_sync(1 + g, kGroupThreads); }
-__device__ __forceinline__ void table_acquire(int g) { bar_sync(3 + g, kPingPongThreads); }
-__device__ __forceinline__ void table_release(int g) { bar_arrive(3 + (g ^ 1), kPingPongThreads); }
-
-// ---- Token ring over one shared-memory table (K2, K3) -------------------------------------------
+// ---- Token ring over one shared-memory table (K2; K3 hands its table over with named barriers) -------------------------------------------
 // The 65,536-bin table leaves room for one CTA per SM.  Its 1,024 threads are split into NG
 // groups (2, 4 or 8) that work on NG different tiles; the table is handed round-robin from group
 // to group through mbarriers: token[g] completes a phase when every thread of group g-1 has
@@ -210,17 +199,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-// shared -> global bulk store of a contiguous record; generic-proxy writes to the source must be
-// fenced (bulk_fence_smem) before the issuing thread starts the copy, and the source may be
-// rewritten once bulk_wait_read() has returned in that thread
-__device__ __forceinline__ void bulk_fence_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 // exact warp sum of 64-bit integers with three 21-bit limbs (REDUX.ADD is one instruction)
 __device__ __forceinline__ unsigned long long warp_sum_redux(unsigned long long v) {
     const uint32_t l0 = (uint32_t)v & 0x1fffffu, l1 = (uint32_t)(v >> 21) & 0x1fffffu;

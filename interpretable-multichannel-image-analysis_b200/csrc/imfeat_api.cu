@@ -8,6 +8,7 @@
 
 #include "../../include/imfeat.h"
 #include "aux_kernels.cuh"
+#include "post_kernels.cuh"
 #include "common.cuh"
 #include "k1_moments.cuh"
 #include "k2_order_entropy.cuh"
@@ -408,6 +409,44 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
 }
 
 extern "C" {
+
+int imfeat_minmax_fit_device(imfeat_ctx* ctx, const double* d_table, int64_t n_rows, int32_t n_cols,
+                             int64_t row_stride, double* d_stats, void* stream) {
+    if (!ctx) return fail(nullptr, IMFEAT_ERR_ARG, "ctx is NULL");
+    if (n_rows < 0 || n_cols <= 0 || row_stride < n_cols) return fail(ctx, IMFEAT_ERR_ARG, "bad table shape");
+    if (!d_stats || (n_rows > 0 && !d_table)) return fail(ctx, IMFEAT_ERR_ARG, "NULL table or stats pointer");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = (int)(n_rows < kPostRowBlocks ? (n_rows > 0 ? n_rows : 1) : kPostRowBlocks);
+    double* partial = nullptr;
+    CU(cudaMallocAsync((void**)&partial, sizeof(double) * 2 * (size_t)blocks * n_cols, st));
+    const dim3 grid((n_cols + 127) / 128, blocks);
+    colstats_partial_kernel<<<grid, 128, 0, st>>>(d_table, n_rows, n_cols, row_stride, partial);
+    minmax_finish_kernel<<<(n_cols + 127) / 128, 128, 0, st>>>(partial, blocks, n_cols, d_stats);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(partial, st));
+    return IMFEAT_OK;
+}
+
+int imfeat_minmax_transform_device(imfeat_ctx* ctx, const double* d_in, int64_t n_rows, int32_t n_cols,
+                                   int64_t row_stride_in, const double* d_stats, double* d_out,
+                                   int64_t row_stride_out, void* stream) {
+    if (!ctx) return fail(nullptr, IMFEAT_ERR_ARG, "ctx is NULL");
+    if (n_rows < 0 || n_cols <= 0 || row_stride_in < n_cols || row_stride_out < n_cols)
+        return fail(ctx, IMFEAT_ERR_ARG, "bad table shape");
+    if (n_rows == 0) return IMFEAT_OK;
+    if (!d_in || !d_out || !d_stats) return fail(ctx, IMFEAT_ERR_ARG, "NULL pointer");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)n_rows * n_cols;
+    const long long want = (total + 255) / 256, cap = 8ll * ctx->sm_count;
+    minmax_apply_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(d_in, n_rows, n_cols, row_stride_in, d_stats,
+                                                                       d_out, row_stride_out);
+    ctx->launches += 1;
+    CU(cudaGetLastError());
+    return IMFEAT_OK;
+}
 
 int imfeat_enable_timing(imfeat_ctx* ctx, int32_t enable) {
     if (!ctx) return fail(nullptr, IMFEAT_ERR_ARG, "ctx is NULL");

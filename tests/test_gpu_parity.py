@@ -427,3 +427,35 @@ def test_wide_range_tiles_through_host_pipeline(torch_mod):
     planes = torch.from_numpy(_planar(img)).cuda()
     dev = ex.extract_planar(planes).cpu().numpy()
     assert np.array_equal(got, dev, equal_nan=True)
+
+
+def test_minmax_scaler_matches_sklearn(torch_mod):
+    """NB:389-394: fit on the training rows, transform training and test rows; against sklearn itself,
+    bit for bit (same two roundings), NaN cells and constant / all-NaN columns included."""
+    torch = torch_mod
+    from sklearn.preprocessing import MinMaxScaler as SkScaler
+    import warnings
+    rng = np.random.default_rng(21)
+    ex = imf.get_extractor(four_directions=True, shape=True, moments=True)
+    planes, masks, _ = ex.synth(5, 0, 300, 6, 64, 64, with_masks=True)
+    table = ex.extract_planar(planes, masks, hs=64, ws=64)          # stays on the device
+    # make the table nasty: a constant column, an all-NaN column, scattered NaN
+    table[:, 3] = 7.25
+    table[:, 5] = float("nan")
+    table[rng.integers(0, 300, 40), rng.integers(0, table.shape[1], 40)] = float("nan")
+    X = table.cpu().numpy()
+    tr, te = X[:225], X[225:]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sk = SkScaler().fit(tr)
+        want_tr, want_te = sk.transform(tr), sk.transform(te)
+    sc = imf.MinMaxScaler().fit(table[:225])
+    got_tr = sc.transform(table[:225]).cpu().numpy()
+    got_te = sc.transform(table[225:]).cpu().numpy()
+    for name in ("data_min_", "data_max_", "scale_", "min_"):
+        g, w = getattr(sc, name).cpu().numpy(), getattr(sk, name)
+        assert np.array_equal(g, w, equal_nan=True), name
+    assert np.array_equal(got_tr, want_tr, equal_nan=True)
+    assert np.array_equal(got_te, want_te, equal_nan=True)
+    # numpy front door
+    assert np.array_equal(imf.MinMaxScaler().fit_transform(tr), want_tr, equal_nan=True)
