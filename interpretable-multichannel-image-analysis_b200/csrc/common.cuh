@@ -29,6 +29,7 @@ struct Params {
     uint32_t* status;          // nullable
     const double* log2tab;     // log2(k), k = 0..kMaxPixels (k=0 -> 0)
     unsigned int* sched;       // per-call work counters, one per kernel (dynamic tile scheduling)
+    int k1_fp64_only;          // IMFEAT_K1_FP64=1: skip K1's integer pass (testing the fallback)
     const unsigned long long* gfix;  // round(2^42 * ((k+1)*log2(k+1) - k*log2(k))), k < kMaxPixels
     uint32_t* counts;          // nullable: GLCM bin dump [tile][angle][65536]
     long long n_tiles;

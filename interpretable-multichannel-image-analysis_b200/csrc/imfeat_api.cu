@@ -311,6 +311,7 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
     // may be in flight at the same time)
     P.sched = ctx->d_sched + 8 * (ctx->sched_head++ % kSchedSlots);
     CU(cudaMemsetAsync(P.sched, 0, sizeof(unsigned int) * 8, st));
+    { const char* e1 = getenv("IMFEAT_K1_FP64"); P.k1_fp64_only = (e1 && atoi(e1) != 0) ? 1 : 0; }
     int slot = -1;
     if (ctx->timing) {
         slot = ctx->t_head;

@@ -5,8 +5,10 @@
 //
 // Single pass over HBM.  min / max / sum use packed 16-bit SIMD (2 pixels per instruction).  The
 // central moments are accumulated around an integer pivot p taken from a small sample of the
-// tile (the mean of ~256 valid pixels): y = x - p is formed exactly as a double by one
-// integer multiply-add into the mantissa of 2^52, then sum y^2 (exact), y^3, y^4 with FP64 FMAs.
+// tile (the mean of ~256 valid pixels), y = x - p: as exact 64-bit integers (IMAD.WIDE) while
+// |y| <= 11,585 -- all 12-bit data -- and otherwise, in a second pass over the tile, as doubles
+// (y formed exactly by an integer add into the mantissa of 2^52, then sum y^2 (exact), y^3, y^4
+// with FP64 FMAs).
 // The pivot is shifted to the exact mean analytically in the epilogue; because the pivot is the
 // mean of a subset of the pixels, |mean - p| is bounded by a small multiple of the standard
 // deviation and the shift is numerically benign.
@@ -74,6 +76,59 @@ __device__ __forceinline__ void k1_vec(const uint4& v, const uint2& m, unsigned 
             k1_px(w[k] >> 16, c64, st.S[3], st.S[4], st.S[5]);
         }
     }
+}
+
+// ---- integer variant of the central sums -----------------------------------------------------------
+// While |x - p| <= kK1IntLimit for every pixel of the tile, the three sums are exact integers that fit
+// 64 bits per lane (up to 1,024 pixels per lane): y^2 in 32 bits (eight of them are added in 32 bits
+// before they go into the 64-bit sum), y^3 by a signed and y^4 by an unsigned 32x32->64 multiply-add.
+// That is 7 issue slots per pixel instead of 12 with FP64.  Whether the limit held is known only
+// after the pass (from min and max); a tile that breaks it is done again with the FP64 loop.
+constexpr int kK1IntLimit = 11585;                       // floor(2^13.5): 1,024 * y^4 < 2^64
+
+struct K1IntState {
+    uint32_t mn2, mx2, sum, cnt;
+    unsigned long long S2;
+    long long S3[2];
+    unsigned long long S4[2];
+};
+
+__device__ __forceinline__ void k1_px_int(int y, uint32_t& s2, long long& S3, unsigned long long& S4) {
+    const uint32_t y2 = (uint32_t)y * (uint32_t)y;      // exact below the limit, discarded above it
+    s2 += y2;
+    S3 += (long long)(int)y2 * (long long)y;             // IMAD.WIDE
+    S4 += (unsigned long long)y2 * (unsigned long long)y2;   // IMAD.WIDE.U32
+}
+
+template <bool MASKED>
+__device__ __forceinline__ void k1_vec_int(const uint4& v, const uint2& m, int p, K1IntState& st) {
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t h[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    if (MASKED) {
+        mask_halfwords(m.x, h[0], h[1]);
+        mask_halfwords(m.y, h[2], h[3]);
+        st.cnt += (__popc(h[0]) + __popc(h[1]) + __popc(h[2]) + __popc(h[3])) >> 4;
+    }
+    uint32_t s2 = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (MASKED) {
+            st.mn2 = __vminu2(st.mn2, w[k] | ~h[k]);
+            w[k] &= h[k];
+        } else {
+            st.mn2 = __vminu2(st.mn2, w[k]);
+        }
+        st.mx2 = __vmaxu2(st.mx2, w[k]);
+        st.sum = __dp2a_lo(w[k], 0x0101u, st.sum);
+        int y0 = (int)(w[k] & 0xffffu) - p, y1 = (int)(w[k] >> 16) - p;
+        if (MASKED) {                                      // outside the mask: y = 0 adds nothing
+            y0 &= (int)__byte_perm(h[k], 0u, 0x1010);
+            y1 &= (int)__byte_perm(h[k], 0u, 0x3232);
+        }
+        k1_px_int(y0, s2, st.S3[0], st.S4[0]);
+        k1_px_int(y1, s2, st.S3[1], st.S4[1]);
+    }
+    st.S2 += s2;
 }
 
 __device__ __forceinline__ void k1_epilogue(const Params& P, const Tile& T, uint32_t n_eff,
@@ -176,7 +231,58 @@ __global__ void __launch_bounds__(256) k1_moments_kernel(const __grid_constant__
         const long long p = scnt ? (long long)((ssum + (scnt >> 1)) / scnt) : 0;
         const unsigned long long c64 = (0x43300000ull << 32) | (unsigned long long)((1u << 20) - (uint32_t)p);
 
-        // ---- the streaming pass ----
+        // ---- the streaming pass: exact integer sums first (see K1IntState) ----
+        bool done = false;
+        if (!P.k1_fp64_only) {
+            K1IntState st;
+            st.mn2 = 0xffffffffu; st.mx2 = 0u; st.sum = 0u; st.cnt = 0u;
+            st.S2 = 0ull; st.S3[0] = 0; st.S3[1] = 0; st.S4[0] = 0ull; st.S4[1] = 0ull;
+            const int pi = (int)p;
+            constexpr int kU = kK1Unroll;                  // loads in flight per lane (8 measured no faster)
+            int idx = lane;
+            for (; idx + 32 * (kU - 1) < nfull; idx += 32 * kU) {
+                uint4 v[kU];
+                uint2 m[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    v[u] = ld_stream(px4 + idx + 32 * u);
+                    m[u] = make_uint2(0u, 0u);
+                    if (MASKED) m[u] = __ldg(mk2 + idx + 32 * u);
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) k1_vec_int<MASKED>(v[u], m[u], pi, st);
+            }
+            for (; idx < nfull; idx += 32) {
+                const uint4 v = ld_stream(px4 + idx);
+                uint2 m = make_uint2(0u, 0u);
+                if (MASKED) m = __ldg(mk2 + idx);
+                k1_vec_int<MASKED>(v, m, pi, st);
+            }
+            if (tail_ok) {
+                st.mn2 = __vminu2(st.mn2, xt | 0xffff0000u);
+                st.mx2 = __vmaxu2(st.mx2, xt);
+                st.sum += xt;
+                st.cnt += 1;
+                uint32_t s2 = 0u;
+                k1_px_int((int)xt - pi, s2, st.S3[0], st.S4[0]);
+                st.S2 += s2;
+            }
+            const uint32_t total = __reduce_add_sync(0xffffffffu, st.sum);
+            const uint32_t n_eff = MASKED ? __reduce_add_sync(0xffffffffu, st.cnt) : (uint32_t)T.n;
+            const uint32_t vmin = __reduce_min_sync(0xffffffffu, min(st.mn2 & 0xffffu, st.mn2 >> 16));
+            const uint32_t vmax = __reduce_max_sync(0xffffffffu, max(st.mx2 & 0xffffu, st.mx2 >> 16));
+            // did every |x - p| stay within the limit?  (no pixel inside the mask: nothing was added)
+            if (n_eff == 0 || ((int)vmax - pi <= kK1IntLimit && pi - (int)vmin <= kK1IntLimit)) {
+                const unsigned long long S2 = warp_sum_redux(st.S2);
+                const long long S3 = (long long)warp_sum_redux((unsigned long long)(st.S3[0] + st.S3[1]));
+                const unsigned long long S4 = warp_sum_redux(st.S4[0] + st.S4[1]);
+                if (lane == 0) k1_epilogue(P, T, n_eff, vmin, vmax, total, p, (double)S2, (double)S3, (double)S4);
+                done = true;
+            }
+        }
+        if (done) continue;
+
+        // ---- fallback: the same pass with FP64 sums (any 16-bit range) ----
         K1State st;
         st.mn2 = 0xffffffffu; st.mx2 = 0u; st.sum = 0u; st.cnt = 0u;
 #pragma unroll

@@ -459,3 +459,22 @@ def test_minmax_scaler_matches_sklearn(torch_mod):
     assert np.array_equal(got_te, want_te, equal_nan=True)
     # numpy front door
     assert np.array_equal(imf.MinMaxScaler().fit_transform(tr), want_tr, equal_nan=True)
+
+
+def test_k1_wide_range_falls_back_to_fp64(torch_mod):
+    """K1 sums (x - pivot)^k as exact integers while |x - pivot| <= 11,585 and repeats the tile with FP64
+    sums otherwise: tiles on both sides of the limit, and just around it, against the C oracle."""
+    rng = np.random.default_rng(31)
+    h, w = 64, 64
+    planes = []
+    for spread in (100, 11000, 11580, 11590, 12000, 30000, 65535):
+        base = rng.integers(0, 65536 - spread) if spread < 65535 else 0
+        x = base + rng.integers(0, spread + 1, (h, w))
+        x[0, 0], x[-1, -1] = base, base + spread            # the extremes are really there
+        planes.append(x.astype(np.uint16))
+    img = np.stack(planes, axis=2)[None]
+    mask = (rng.random(img.shape) < 0.8).astype(np.uint8)
+    cols = imf.feature_columns(img.shape[3])
+    compare_tables(imf.extract_features(img), c_oracle.table(_planar(img)), cols, label="k1 range")
+    compare_tables(imf.extract_features(img, mask), c_oracle.table(_planar(img), _planar(mask)), cols,
+                   label="k1 range masked")
