@@ -131,14 +131,24 @@ __device__ __forceinline__ void k1_vec_int(const uint4& v, const uint2& m, int p
     st.S2 += s2;
 }
 
-__device__ __forceinline__ void k1_epilogue(const Params& P, const Tile& T, uint32_t n_eff,
+// One tile's finished sums, parked until 32 of them can be turned into features by 32 lanes at once:
+// the epilogue is ~250 instructions of FP64 divisions and square roots, a fifth of the per-tile cost
+// when a single lane runs it.
+struct K1Pending {
+    double* o;                  // out_row + col_basic + 17 * slot
+    uint32_t* status;
+    uint32_t n_eff, vmin, vmax, total;
+    long long p;
+    double S2, S3, S4;
+};
+
+__device__ __forceinline__ void k1_epilogue(double* o, uint32_t* status, uint32_t n_eff,
                                             uint32_t vmin, uint32_t vmax, uint32_t total,
                                             long long p, double S2, double S3, double S4) {
-    double* o = T.out_row + P.col_basic + kNBasic * T.slot;
     if (n_eff == 0) {
         const double nan = qnan();
         o[0] = nan; o[10] = nan; o[11] = nan; o[12] = nan; o[13] = nan; o[14] = nan; o[15] = nan;
-        if (T.status) atomicOr(T.status, kStEmptyMask);
+        if (status) atomicOr(status, kStEmptyMask);
         return;
     }
     const double nn = (double)n_eff;
@@ -160,11 +170,30 @@ __device__ __forceinline__ void k1_epilogue(const Params& P, const Tile& T, uint
         o[13] = (vmin == vmax) ? 0.0 : o[13];
         o[14] = qnan();
         o[15] = qnan();
-        if (T.status) atomicOr(T.status, kStConstant);
+        if (status) atomicOr(status, kStConstant);
     } else {
         o[14] = m4 / (m2 * m2) - 3.0;
         o[15] = m3 / (m2 * sqrt(m2));
     }
+}
+
+__device__ __forceinline__ void k1_epilogue(const Params& P, const Tile& T, uint32_t n_eff, uint32_t vmin,
+                                            uint32_t vmax, uint32_t total, long long p, double S2, double S3, double S4) {
+    k1_epilogue(T.out_row + P.col_basic + kNBasic * T.slot, T.status, n_eff, vmin, vmax, total, p, S2, S3, S4);
+}
+__device__ __forceinline__ void k1_park(K1Pending* slot, const Params& P, const Tile& T, uint32_t n_eff, uint32_t vmin,
+                                        uint32_t vmax, uint32_t total, long long p, double S2, double S3, double S4) {
+    slot->o = T.out_row + P.col_basic + kNBasic * T.slot; slot->status = T.status;
+    slot->n_eff = n_eff; slot->vmin = vmin; slot->vmax = vmax; slot->total = total;
+    slot->p = p; slot->S2 = S2; slot->S3 = S3; slot->S4 = S4;
+}
+__device__ __forceinline__ void k1_flush(const K1Pending* slots, int count, int lane) {
+    __syncwarp();
+    if (lane < count) {
+        const K1Pending q = slots[lane];
+        k1_epilogue(q.o, q.status, q.n_eff, q.vmin, q.vmax, q.total, q.p, q.S2, q.S3, q.S4);
+    }
+    __syncwarp();
 }
 
 template <bool MASKED>
@@ -174,6 +203,9 @@ __global__ void __launch_bounds__(256) k1_moments_kernel(const __grid_constant__
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
 
     (void)warp0; (void)nwarps;
+    __shared__ K1Pending pending_all[8][32];               // 256-thread CTAs: one row per warp
+    K1Pending* pending = pending_all[threadIdx.x >> 5];
+    int n_pending = 0;
     long long tnext = next_tile(P.sched + 0);
     while (tnext < P.n_tiles) {
         const long long t = tnext;
@@ -276,7 +308,8 @@ __global__ void __launch_bounds__(256) k1_moments_kernel(const __grid_constant__
                 const unsigned long long S2 = warp_sum_redux(st.S2);
                 const long long S3 = (long long)warp_sum_redux((unsigned long long)(st.S3[0] + st.S3[1]));
                 const unsigned long long S4 = warp_sum_redux(st.S4[0] + st.S4[1]);
-                if (lane == 0) k1_epilogue(P, T, n_eff, vmin, vmax, total, p, (double)S2, (double)S3, (double)S4);
+                if (lane == 0) k1_park(pending + n_pending, P, T, n_eff, vmin, vmax, total, p, (double)S2, (double)S3, (double)S4);
+                if (++n_pending == 32) { k1_flush(pending, 32, lane); n_pending = 0; }
                 done = true;
             }
         }
@@ -322,8 +355,10 @@ __global__ void __launch_bounds__(256) k1_moments_kernel(const __grid_constant__
         const double S2 = warp_sum(st.S[0] + st.S[3]);
         const double S3 = warp_sum(st.S[1] + st.S[4]);
         const double S4 = warp_sum(st.S[2] + st.S[5]);
-        if (lane == 0) k1_epilogue(P, T, n_eff, vmin, vmax, total, p, S2, S3, S4);
+        if (lane == 0) k1_park(pending + n_pending, P, T, n_eff, vmin, vmax, total, p, S2, S3, S4);
+        if (++n_pending == 32) { k1_flush(pending, 32, lane); n_pending = 0; }
     }
+    k1_flush(pending, n_pending, lane);
 }
 
 }  // namespace imfeat
