@@ -371,13 +371,38 @@ __global__ void __launch_bounds__(kK4Threads, 3) k4_shape_kernel(const __grid_co
 namespace imfeat {
 
 constexpr int kK4wWords = 1024;     // >= h * ceil(w/32) under the fast-path limits (<= 768)
+constexpr int kK4wBatch = 16;       // finished tiles parked per warp until their epilogues run side by side
+
+// The two epilogues (eigenvalues, square roots, 128-bit central moments: ~700 instructions) were a fifth
+// of the per-tile cost with one lane each; parked, 16 tiles are finished by 32 lanes at once.
+struct K4Pending {
+    double* out_row;
+    uint32_t* status;
+    int slot, rmin, rmax, cmin, cmax, pad;
+    unsigned long long s[9];
+    unsigned long long mq[10];
+};
 
 template <bool MASKED>
 __global__ void __launch_bounds__(32, 20) k4w_shape_kernel(const __grid_constant__ Params P) {
     __shared__ uint32_t mrow[kK4wWords];
     __shared__ uint32_t brow[kK4wWords];
+    __shared__ K4Pending pending[kK4wBatch];
     const int lane = threadIdx.x;
     const bool want_mom = P.col_moment >= 0;
+    int n_pending = 0;
+    auto flush = [&](int count) {
+        __syncwarp();
+        const int k = lane & (kK4wBatch - 1);
+        if (k < count) {
+            const K4Pending& q = pending[k];
+            Tile Tq;
+            Tq.out_row = q.out_row; Tq.status = q.status; Tq.slot = q.slot;
+            if (lane < kK4wBatch) { if (P.col_shape >= 0) k4_shape_epilogue(P, Tq, q.s, q.rmin, q.rmax, q.cmin, q.cmax); }
+            else if (want_mom) k4_moment_epilogue(P, Tq, q.mq);
+        }
+        __syncwarp();
+    };
 
     long long tnext = next_tile(P.sched + 3);
     while (tnext < P.n_tiles) {
@@ -566,10 +591,21 @@ __global__ void __launch_bounds__(32, 20) k4w_shape_kernel(const __grid_constant
 #pragma unroll
             for (int k = 0; k < 10; ++k) mq[k] = warp_sum_redux(mq[k]);
         }
-        if (lane == 0 && P.col_shape >= 0) k4_shape_epilogue(P, T, s, rmin, rmax, cmin, cmax);
-        if (lane == 1 && want_mom) k4_moment_epilogue(P, T, mq);
+        if (lane == 0) {
+            K4Pending& q = pending[n_pending];
+            q.out_row = T.out_row; q.status = T.status; q.slot = T.slot;
+            q.rmin = rmin; q.rmax = rmax; q.cmin = cmin; q.cmax = cmax;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) q.s[k] = s[k];
+            if (want_mom) {
+#pragma unroll
+                for (int k = 0; k < 10; ++k) q.mq[k] = mq[k];
+            }
+        }
+        if (++n_pending == kK4wBatch) { flush(kK4wBatch); n_pending = 0; }
         __syncwarp();                                        // mrow / brow are rewritten by the next tile
     }
+    flush(n_pending);
 }
 
 }  // namespace imfeat
