@@ -286,11 +286,13 @@ static void fill_params(Params& P, imfeat_ctx* ctx, const uint16_t* planes, cons
 static int timing_resolve(imfeat_ctx* ctx, int slot) {
     const unsigned m = ctx->t_mask[slot];
     if (!m) return IMFEAT_OK;
+    static const int kLaunchOrder[4] = {0, 1, 3, 2};       // K1, K2, K4, K3 (see launch_all)
     int last = 0;
-    for (int k = 0; k < 4; ++k) if (m & (1u << k)) last = k + 1;
+    for (int i = 0; i < 4; ++i) if (m & (1u << kLaunchOrder[i])) last = kLaunchOrder[i] + 1;
     CU(cudaEventSynchronize(ctx->t_ev[slot][last]));
     int prev = -1;
-    for (int k = 0; k < 4; ++k) {
+    for (int i = 0; i < 4; ++i) {
+        const int k = kLaunchOrder[i];
         if (!(m & (1u << k))) continue;
         // the start event of kernel k is the most recent event recorded before it
         int start = (prev < 0) ? 0 : prev + 1;
@@ -378,13 +380,9 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
         }
         IMFEAT_MARK(1)
     }
-    if (o->want_glcm) {
-        const int g3 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
-        const int maxpx = ((P.hs * P.ws + 7) & ~7);
-        launch_k3<false>(masked, k3_groups(maxpx, masked), g3, k3_smem_bytes(maxpx, masked), st, P, maxpx);
-        IMFEAT_MARK(2)
-        ctx->launches += 1;
-    }
+    // K4 goes before K3: with several GPUs the all-gather of the previous batch then overlaps the
+    // dynamically scheduled warp-per-tile kernels (K1, K2c, K4w) and is over when K3 starts, whose
+    // persistent one-CTA-per-SM grid would otherwise wait for the SMs the collective holds
     if (o->want_shape || o->want_moments) {
         const char* k4env = getenv("IMFEAT_K4_WARP");
         const bool warp_tiles = P.hs <= kK4FastDim && P.ws <= kK4FastDim && P.hs * P.ws <= kK4FastPixels &&
@@ -402,6 +400,13 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
             else k4_shape_kernel<false><<<g4, kK4Threads, sizeof(K4Smem), st>>>(P);
         }
         IMFEAT_MARK(3)
+        ctx->launches += 1;
+    }
+    if (o->want_glcm) {
+        const int g3 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
+        const int maxpx = ((P.hs * P.ws + 7) & ~7);
+        launch_k3<false>(masked, k3_groups(maxpx, masked), g3, k3_smem_bytes(maxpx, masked), st, P, maxpx);
+        IMFEAT_MARK(2)
         ctx->launches += 1;
     }
 #undef IMFEAT_MARK
