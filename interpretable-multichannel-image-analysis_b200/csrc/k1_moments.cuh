@@ -199,10 +199,6 @@ __device__ __forceinline__ void k1_flush(const K1Pending* slots, int count, int 
 template <bool MASKED>
 __global__ void __launch_bounds__(256) k1_moments_kernel(const __grid_constant__ Params P) {
     const int lane = threadIdx.x & 31;
-    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-
-    (void)warp0; (void)nwarps;
     __shared__ K1Pending pending_all[8][32];               // 256-thread CTAs: one row per warp
     K1Pending* pending = pending_all[threadIdx.x >> 5];
     int n_pending = 0;

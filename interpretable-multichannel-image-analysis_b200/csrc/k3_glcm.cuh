@@ -9,8 +9,8 @@
 //   notebook's float64 expression for every uint16 pair; tests/test_oracle_cpu.py).
 // * the 256x256 bins live in shared memory as 16-bit counters (two per 32-bit word, 128 KB), built
 //   with shared-memory atomics on the pair stream, dumped on request (parity), and only ever
-//   cleared sparsely by re-walking the pairs.  One persistent CTA per SM; its two 512-thread groups
-//   work on two tiles at a time and take turns on the table, handing it over with named barriers
+//   cleared sparsely by re-walking the pairs.  One persistent CTA per SM; its four 256-thread groups
+//   work on four tiles at a time and take turns on the table, handing it over with named barriers
 //   (bar.arrive / bar.sync: the waiting group is parked in hardware and issues nothing).  While one
 //   group owns the table the others load the pair items of their next direction, add up the pair-stream
 //   sums (contrast, dissimilarity, homogeneity, correlation need no bins) and turn the pairs into hits.
@@ -24,7 +24,6 @@
 #include "common.cuh"
 
 namespace imfeat {
-
 
 constexpr int kK3Threads = 1024;     // NG groups of 1024 / NG threads
 
@@ -88,7 +87,7 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 struct K3Acc {
-    uint32_t si, sj, sii, sjj, sij, sd, sasm, m;
+    uint32_t si, sj, sii, sjj, sij, sd, m;
     double hom;
 };
 
@@ -497,7 +496,7 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
             const K3Geom G = k3_geom<MASKED>(tw, P.dr[a], P.dc[a], bx[0], bx[1], bx[2], bx[3]);
             uint32_t hit[kCache][16];
             uint32_t sold = 0u, valid = 0u, np = 0u;
-            K3Acc A = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0};
+            K3Acc A = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0};
             K3AccS& Acc = S.acc[g][buf][a];
             auto sums16 = [&](const uint32_t (&I4)[4], const uint32_t (&J4)[4], uint32_t pm) {
 #pragma unroll
@@ -526,7 +525,7 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
                     const uint32_t lo = (uint32_t)hf, old = atomicAdd(&Acc.hom_lo, lo);
                     atomicAdd(&Acc.hom_hi, (uint32_t)(hf >> 32) + (old + lo < old ? 1u : 0u));
                 }
-                A = K3Acc{0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0};
+                A = K3Acc{0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0};
                 np = 0u;
             };
 #pragma unroll

@@ -289,11 +289,11 @@ def test_full_size_properties(torch_mod):
     assert np.array_equal(t2[::-1], t, equal_nan=True)
     # sampled parity on regenerated objects (host mirror of the device generator)
     from imfeat_b200 import synth
-    pick = np.random.default_rng(0).choice(N, 48, replace=False)
-    for i in pick:
-        img = np.stack([synth.synth_plane(0, int(i), ch, 64, 64)[0] for ch in range(C)], axis=2)[None]
-        want = c_oracle.table(_planar(img), glcm=True, n_angles=4)
-        compare_tables(t[i:i + 1], want, cols, label="sample %d" % i)
+    pick = np.sort(np.random.default_rng(0).choice(N, 1024, replace=False))     # >= 1,024 objects
+    img = np.stack([np.stack([synth.synth_plane(0, int(i), ch, 64, 64)[0] for ch in range(C)], axis=2)
+                    for i in pick])
+    want = c_oracle.table(_planar(img), glcm=True, n_angles=4)
+    compare_tables(t[pick], want, cols, label="1024 sampled objects")
 
 
 def test_custom_percentiles_and_distance(torch_mod):
