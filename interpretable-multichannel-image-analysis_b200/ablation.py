@@ -30,35 +30,72 @@ def permutation_sources(n_objects, n_channels, seed=42):
     return out
 
 
+def sweep_index(planes, mode="loco", seed=42):
+    """The device index tensor of a sweep: channel lists [C, C-1] for "loco", source-object tables
+    [C, N, C] for "permute" (built on the host once, copied once)."""
+    import torch
+    N, C = int(planes.shape[0]), int(planes.shape[1])
+    if mode == "loco":
+        return torch.from_numpy(loco_channel_lists(C)).to(planes.device)
+    if mode == "permute":
+        return torch.from_numpy(permutation_sources(N, C, seed)).to(planes.device)
+    raise ValueError("mode must be 'loco' or 'permute'")
+
+
 def channel_ablation_sweep(extractor, planes, masks=None, sizes=None, hs=None, ws=None,
-                           mode="loco", seed=42, out=None):
+                           mode="loco", seed=42, out=None, index=None):
     """Re-extract once per ablated channel, entirely on the device.
 
     mode "loco"    -> tensor [C, N, row_width(C-1)]  (column suffixes are positional, NB:241;
                       ``FeatureExtractor.columns(C-1, channel_ids=...)`` restores original ids)
     mode "permute" -> tensor [C, N, row_width(C)]; permuting objects is only meaningful for
                       equal-size objects, so ``sizes`` must be None.
+    ``index`` is the tensor ``sweep_index`` returns (built here when not given).
     """
     import torch
     N, C = int(planes.shape[0]), int(planes.shape[1])
     dev = planes.device
+    if mode == "permute" and sizes is not None:
+        raise ValueError("channel permutation across objects needs equal-size objects")
+    if index is None:
+        index = sweep_index(planes, mode, seed)
     if mode == "loco":
-        lists = torch.from_numpy(loco_channel_lists(C)).to(dev)
         width = extractor.row_width(C - 1)
         res = out if out is not None else torch.empty((C, N, width), dtype=torch.float64, device=dev)
         for k in range(C):
-            extractor.extract_planar(planes, masks, sizes, hs=hs, ws=ws, chan=lists[k], out=res[k])
+            extractor.extract_planar(planes, masks, sizes, hs=hs, ws=ws, chan=index[k], out=res[k])
         return res
     if mode == "permute":
-        if sizes is not None:
-            raise ValueError("channel permutation across objects needs equal-size objects")
-        src = torch.from_numpy(permutation_sources(N, C, seed)).to(dev)
         width = extractor.row_width(C)
         res = out if out is not None else torch.empty((C, N, width), dtype=torch.float64, device=dev)
         for k in range(C):
-            extractor.extract_planar(planes, masks, None, hs=hs, ws=ws, src_obj=src[k], out=res[k])
+            extractor.extract_planar(planes, masks, None, hs=hs, ws=ws, src_obj=index[k], out=res[k])
         return res
     raise ValueError("mode must be 'loco' or 'permute'")
+
+
+class CapturedSweep:
+    """A whole channel-ablation sweep captured once into a CUDA graph: ``replay()`` re-runs the C
+    re-extractions (5 kernels each) on the current contents of ``planes`` / ``masks`` with a single
+    launch and no host work in between -- e.g. once per bootstrap replicate or per augmented copy
+    written into the same buffers.  The index tensors, the output block and the extractor's internal
+    buffers are fixed at capture time; per-kernel timing must be off while capturing."""
+
+    def __init__(self, extractor, planes, masks=None, sizes=None, hs=None, ws=None, mode="loco", seed=42):
+        import torch
+        self.extractor, self.planes, self.masks = extractor, planes, masks
+        self.index = sweep_index(planes, mode, seed)
+        kw = dict(sizes=sizes, hs=hs, ws=ws, mode=mode, seed=seed, index=self.index)
+        # one eager run sizes the extractor's internal buffers (nothing may be allocated while capturing)
+        self.out = channel_ablation_sweep(extractor, planes, masks, **kw)
+        torch.cuda.synchronize(planes.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            channel_ablation_sweep(extractor, planes, masks, out=self.out, **kw)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
 
 
 def channel_importance_from_sweep(base_score, ablated_scores):

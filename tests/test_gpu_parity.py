@@ -374,6 +374,29 @@ def test_ablation_sweep_driver(torch_mod):
         assert np.array_equal(perm[k], want, equal_nan=True)
 
 
+def test_ablation_sweep_cuda_graph(torch_mod):
+    """The sweep captured into a CUDA graph: replays follow the current contents of the input buffers."""
+    torch = torch_mod
+    from imfeat_b200 import ablation
+    ex = imf.get_extractor(four_directions=True, shape=True, moments=True)
+    C, N = 4, 200
+    planes, masks, _ = ex.synth(12, 0, N, C, 64, 64)
+    for mode in ("loco", "permute"):
+        cap = ablation.CapturedSweep(ex, planes, masks, hs=64, ws=64, mode=mode)
+        want = ablation.channel_ablation_sweep(ex, planes, masks, hs=64, ws=64, mode=mode)
+        assert torch.equal(cap.replay().view(torch.int64), want.view(torch.int64))
+        # new objects written into the same buffers, one launch
+        p2, m2, _ = ex.synth(13, 0, N, C, 64, 64)
+        keep_p, keep_m = planes.clone(), masks.clone()
+        planes.copy_(p2); masks.copy_(m2)
+        want2 = ablation.channel_ablation_sweep(ex, planes, masks, hs=64, ws=64, mode=mode)
+        got2 = cap.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(got2.view(torch.int64), want2.view(torch.int64))
+        assert not torch.equal(want2.view(torch.int64), want.view(torch.int64))
+        planes.copy_(keep_p); masks.copy_(keep_m)
+
+
 def test_repeatability(torch_mod):
     """Same inputs, different launches / streams: identical bits (integer accumulation everywhere
     order could matter)."""
