@@ -47,6 +47,8 @@ struct imfeat_ctx {
     void* dev_out[2];
     size_t in_bytes, out_bytes;
     // optional per-kernel timing (imfeat_enable_timing): a ring of event sets, resolved lazily
+    // debugging / measurement switches, read from the environment once at imfeat_create
+    int env_k1_fp64, env_k1_tma, env_k2_compact, env_k4_warp, env_k2_groups;
     int timing;
     int t_head, t_pending;
     cudaEvent_t t_ev[kTimingSlots][5];
@@ -120,6 +122,15 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
     ctx = (imfeat_ctx*)calloc(1, sizeof(imfeat_ctx));
     if (!ctx) return fail(nullptr, IMFEAT_ERR_NOMEM, "out of host memory");
     ctx->device = device;
+    {
+        auto flag = [](const char* name, int def) { const char* e = getenv(name); return e ? atoi(e) : def; };
+        ctx->env_k1_fp64 = flag("IMFEAT_K1_FP64", 0);      // 1: skip K1's integer pass (exercises the FP64 pass)
+        ctx->env_k1_tma = flag("IMFEAT_K1_TMA", 0);        // 1: K1 through the cp.async.bulk ring (unmasked)
+        ctx->env_k2_compact = flag("IMFEAT_K2_COMPACT", 1); // 0: every tile through the full-range ring kernel
+        ctx->env_k4_warp = flag("IMFEAT_K4_WARP", 1);       // 0: CTA-per-tile K4 for every batch
+        const int g2 = flag("IMFEAT_K2_GROUPS", 4);
+        ctx->env_k2_groups = (g2 == 2 || g2 == 4 || g2 == 8) ? g2 : 4;
+    }
     ctx->sm_count = prop.multiProcessorCount;
     // log2 table, computed on the host in double precision (k = 0 maps to 0, never used)
     double* tab = (double*)malloc(sizeof(double) * (kMaxPixels + 1));
@@ -220,13 +231,7 @@ static void launch_k3(bool masked, int ng, int grid, size_t smem, cudaStream_t s
 
 // K2: measured on B200 (10,000 64x64x12 objects): unmasked 1.59 ms with 4 groups vs 1.84 ms with 2;
 // masked (branch-free path) 2.19 ms vs 2.39 ms.
-static int k2_groups(bool masked) {
-    const char* env = getenv("IMFEAT_K2_GROUPS");
-    const int def = 4;
-    (void)masked;
-    const int want = env ? atoi(env) : def;
-    return (want == 2 || want == 4 || want == 8) ? want : def;
-}
+static int k2_groups(const imfeat_ctx* ctx) { return ctx->env_k2_groups; }
 
 // C round(): half away from zero, as skimage's _glcm_loop uses for the pixel offsets.
 static int c_round(double v) { return (int)(v < 0 ? -floor(-v + 0.5) : floor(v + 0.5)); }
@@ -313,7 +318,7 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
     // may be in flight at the same time)
     P.sched = ctx->d_sched + 8 * (ctx->sched_head++ % kSchedSlots);
     CU(cudaMemsetAsync(P.sched, 0, sizeof(unsigned int) * 8, st));
-    { const char* e1 = getenv("IMFEAT_K1_FP64"); P.k1_fp64_only = (e1 && atoi(e1) != 0) ? 1 : 0; }
+    P.k1_fp64_only = ctx->env_k1_fp64 != 0;
     int slot = -1;
     if (ctx->timing) {
         slot = ctx->t_head;
@@ -334,8 +339,7 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
     if (o->want_basic) {
         const long long res1 = sm * (ctx->k1_bps[masked] > 0 ? ctx->k1_bps[masked] : 1);   // one resident wave
         const int g1 = (int)((P.n_tiles + 7) / 8 < res1 ? (P.n_tiles + 7) / 8 : res1);
-        const char* k1env = getenv("IMFEAT_K1_TMA");
-        const bool use_tma = !masked && k1env && atoi(k1env) == 1;   // measured: no faster than the direct path
+        const bool use_tma = !masked && ctx->env_k1_tma == 1;   // measured: no faster than the direct path
         if (use_tma) {
             // shared-memory ring of whole tiles filled by cp.async.bulk; one persistent CTA per SM
             const int stage_bytes = ((P.hs * P.ws * 2 + 127) & ~127);
@@ -348,9 +352,8 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
         else k1_moments_kernel<false><<<g1, 256, 0, st>>>(P);
         IMFEAT_MARK(0)
         const int g2 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
-        const int ng2 = k2_groups(masked);
-        const char* k2cenv = getenv("IMFEAT_K2_COMPACT");
-        if (k2cenv && atoi(k2cenv) == 0) {
+        const int ng2 = k2_groups(ctx);
+        if (ctx->env_k2_compact == 0) {
             // full-range kernel for every tile
             if (masked) k2_order_entropy_kernel<true><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, nullptr, nullptr);
             else k2_order_entropy_kernel<false><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, nullptr, nullptr);
@@ -384,9 +387,8 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
     // dynamically scheduled warp-per-tile kernels (K1, K2c, K4w) and is over when K3 starts, whose
     // persistent one-CTA-per-SM grid would otherwise wait for the SMs the collective holds
     if (o->want_shape || o->want_moments) {
-        const char* k4env = getenv("IMFEAT_K4_WARP");
         const bool warp_tiles = P.hs <= kK4FastDim && P.ws <= kK4FastDim && P.hs * P.ws <= kK4FastPixels &&
-                                !(k4env && atoi(k4env) == 0);
+                                ctx->env_k4_warp != 0;
         if (warp_tiles) {
             // every tile of this batch fits the fast path: one warp per tile, many warps per SM
             const long long resw = sm * (ctx->k4w_bps[masked] > 0 ? ctx->k4w_bps[masked] : 1);
