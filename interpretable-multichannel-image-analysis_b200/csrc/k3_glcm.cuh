@@ -39,11 +39,15 @@ __host__ __device__ inline size_t k3_raw_bytes(int max_pixels, bool masked) {
     return ((size_t)max_pixels * 2 + (masked ? (size_t)max_pixels : 0) + 15) & ~(size_t)15;
 }
 
-// What the first warp of a group announces about the group's next tile while the current one is under way.
+// What a group notes about its next tile while the current one is under way.
 struct K3TileInfo {
     int h, w;
     uint32_t row, slot;              // output row, channel slot
-    uint32_t mul, sh, fast, pad;     // quantiser constants (k3_magic / k3_magic_fast) when K1's maximum is known
+    uint32_t mul, sh, fast;          // quantiser constants (k3_magic / k3_magic_fast) when K1's maximum is known
+    int n16, n8;                     // 16-byte pixel chunks / 8-byte mask chunks to prefetch
+    int pad;
+    const uint16_t* px;              // where the prefetch copies read
+    const uint8_t* mk;
 };
 // per group and direction, summed over the warps of the group
 struct K3AccS {
@@ -59,6 +63,7 @@ struct alignas(16) K3Smem {                    // the staging buffers behind it 
     int box[4][2][4];                           // mask bounding box per group and tile parity: rmin rmax cmin cmax
     uint32_t wmax[4][32];                       // per-warp maxima (only when K1 did not run)
     K3TileInfo info[4][2];                      // per group and tile parity
+    uint32_t tileid[4][2][2];                   // output row and channel slot of the tile whose epilogue is still due
 };
 struct K3Group {                               // where the quantised tile and its mask bits live
     uint32_t* q8;                              // quantised pixels (bytes) + slack for unaligned reads
@@ -335,26 +340,29 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
     const uint32_t t_step = NG * gridDim.x;
     uint32_t t = first + g * gridDim.x;                    // this round's tile
     if (g == NG - 1) bar_arrive(1 + NG, 2 * gthreads);     // the table starts out free for group 0
-    // The first warp of a group announces the group's next tile while the current one is under way: it
-    // starts the copy of the raw pixels and mask bytes into the prefetch buffer, notes the geometry,
-    // and fetches K1's maximum, from which lane 0 derives the quantiser constants before the
-    // end-of-tile barrier (publish).
+    // While a tile is under way the group prepares its next one: one lane (of the last warp, the least
+    // loaded one) resolves it -- geometry, source pointers, K1's maximum (the load stays in flight until
+    // publish() turns it into quantiser constants before the end-of-tile barrier) --, then every thread
+    // starts its share of the cp.async copies of the raw pixels and mask bytes into the prefetch buffer.
+    constexpr int gwarps = gthreads / 32;
+    const bool scout = gw == gwarps - 1 && lane == 0;
     double vnext = 0.0;
-    auto announce = [&](uint32_t tile, int nb) {
+    auto resolve = [&](uint32_t tile, int nb) {            // scout only
         const Tile T = resolve_tile(P, tile);
-        if (prefetch) {
-            const int n16 = (T.n * 2 + 15) >> 4, n8 = (T.n + 7) >> 3;
-            for (int k = lane; k < n16; k += 32) cp_async16(raw + 16 * k, reinterpret_cast<const unsigned char*>(T.px) + 16 * k);
-            if (MASKED)
-                for (int k = lane; k < n8; k += 32) cp_async8(raw + 2 * (size_t)max_pixels + 8 * k, T.mk + 8 * k);
-        }
-        if (lane == 0) {
-            K3TileInfo& I = S.info[g][nb];
-            I.h = T.h; I.w = T.w; I.slot = (uint32_t)T.slot; I.row = tile / (uint32_t)P.c_out;
-            if (k1_max) vnext = T.out_row[P.col_basic + kNBasic * T.slot + 10];
-        }
+        K3TileInfo& I = S.info[g][nb];
+        I.h = T.h; I.w = T.w; I.slot = (uint32_t)T.slot; I.row = tile / (uint32_t)P.c_out;
+        I.px = T.px; I.mk = T.mk; I.n16 = (T.n * 2 + 15) >> 4; I.n8 = (T.n + 7) >> 3;
+        if (k1_max) vnext = T.out_row[P.col_basic + kNBasic * T.slot + 10];
     };
-    auto publish = [&](int nb) {                           // lane 0 of the first warp
+    auto start_copies = [&](int nb) {                      // every thread of the group
+        if (!prefetch) return;
+        const K3TileInfo& I = S.info[g][nb];
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(I.px);
+        for (int k = gt; k < I.n16; k += gthreads) cp_async16(raw + 16 * k, src + 16 * k);
+        if (MASKED)
+            for (int k = gt; k < I.n8; k += gthreads) cp_async8(raw + 2 * (size_t)max_pixels + 8 * k, I.mk + 8 * k);
+    };
+    auto publish = [&](int nb) {                           // scout only
         if (!k1_max) return;
         K3TileInfo& I = S.info[g][nb];
         const uint32_t vmax = (vnext == vnext) ? (uint32_t)vnext : 0u;   // NaN: empty mask, no pair exists anyway
@@ -363,20 +371,37 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
         if (!fast) k3_magic(vmax, mul, sh);
         I.mul = mul; I.sh = sh; I.fast = fast ? 1u : 0u;
     };
-    if (gw == 0 && my_count) {
-        announce(t, 0);
-        cp_async_wait_all();
-        if (lane == 0) publish(0);
-    }
+    // The epilogue of a tile (FP64 divisions and square roots, one lane per direction): lane 0 of the last
+    // warps, one direction each.
+    auto epilogue_of = [&](int eb) {
+        const int d = gwarps - 1 - gw;
+        if (d < P.n_angles && lane == 0) {
+            const uint32_t row = S.tileid[g][eb][0];
+            K3AccS& Acc = S.acc[g][eb][d];
+            k3_epilogue(P, P.out + (long long)row * P.row_stride, P.status ? P.status + row : nullptr,
+                        (int)S.tileid[g][eb][1], d, Acc);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) Acc.s[k] = 0u;
+            Acc.hom_lo = 0u; Acc.hom_hi = 0u;
+            Acc.np = 0u;
+        }
+    };
+    if (scout && my_count) resolve(t, 0);
+    bar_sync(id_sync, gthreads);
+    if (my_count) start_copies(0);
+    cp_async_wait_all();
+    if (scout && my_count) publish(0);
     bar_sync(id_sync, gthreads);
 
     for (uint32_t j = 0; j < n_iter; ++j, t += t_step) {
         const bool active = j < my_count;
         const int buf = (int)(j & 1u);
         int tw = 0, th = 0;
+        if (scout && j + 1 < my_count) resolve(t + t_step, buf ^ 1);
         if (active) {
             const K3TileInfo& I = S.info[g][buf];
             tw = I.w; th = I.h;
+            if (gt == 0) { S.tileid[g][buf][0] = I.row; S.tileid[g][buf][1] = I.slot; }
             const int tn = th * tw;
             // pixels and mask bytes: from the prefetch buffer, or straight from global memory
             const uint16_t* pxs = reinterpret_cast<const uint16_t*>(raw);
@@ -484,7 +509,7 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
             }
         }
         bar_sync(id_sync, gthreads);                       // this tile staged
-        if (gw == 0 && j + 1 < my_count) announce(t + t_step, buf ^ 1);   // the raw buffer is free again
+        if (j + 1 < my_count) start_copies(buf ^ 1);       // the raw buffer is free again
         // box of pixels that can take part in a pair: the tile, or the mask's bounding box
         int bx[4] = {0, th - 1, 0, tw - 1};
         if (MASKED && active) { bx[0] = S.box[g][buf][0]; bx[1] = S.box[g][buf][1]; bx[2] = S.box[g][buf][2]; bx[3] = S.box[g][buf][3]; }
@@ -587,21 +612,10 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
             const uint32_t so = __reduce_add_sync(0xffffffffu, sold);
             if (lane == 0 && so) atomicAdd(&Acc.s[6], so);
         }
-        if (gw == 0 && j + 1 < my_count) {
-            cp_async_wait_all();
-            if (lane == 0) publish(buf ^ 1);
-        }
-        bar_sync(id_sync, gthreads);                       // sums final, staging buffers free, next tile announced
-        if (active && gw < P.n_angles && lane == 0) {
-            const uint32_t row = S.info[g][buf].row;
-            k3_epilogue(P, P.out + (long long)row * P.row_stride, P.status ? P.status + row : nullptr,
-                        (int)S.info[g][buf].slot, gw, S.acc[g][buf][gw]);
-            K3AccS& Acc = S.acc[g][buf][gw];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) Acc.s[k] = 0u;
-            Acc.hom_lo = 0u; Acc.hom_hi = 0u;
-            Acc.np = 0u;
-        }
+        cp_async_wait_all();
+        if (scout && j + 1 < my_count) publish(buf ^ 1);
+        bar_sync(id_sync, gthreads);                       // sums final, staging buffers free, next tile prepared
+        if (active) epilogue_of(buf);                      // on the last warps: the scout's warp aside, the least loaded
         if (MASKED && active && gt == 0) {
             S.box[g][buf][0] = 1 << 30; S.box[g][buf][1] = -1; S.box[g][buf][2] = 1 << 30; S.box[g][buf][3] = -1;
         }
