@@ -26,6 +26,7 @@
 namespace imfeat {
 
 constexpr int kK3Threads = 1024;     // NG groups of 1024 / NG threads
+constexpr int kK3Park = 8;           // finished tiles per group whose epilogues run side by side (x directions <= 32 lanes)
 
 // per-group staging buffers behind K3Smem: quantised pixels (one byte each, row-major, + slack for the
 // 16-byte item reads) and mask bits (masked variant only)
@@ -58,12 +59,13 @@ struct K3AccS {
 struct alignas(16) K3Smem {                    // the staging buffers behind it hold 16-byte vectors
     uint32_t hist[32768];
     double homtab[256];                         // 1 / (1 + d^2)
-    K3AccS acc[4][2][kMaxAngles];               // per group, tile parity (the epilogue of a tile overlaps the
-                                                // next tile's first sums) and direction
+    K3AccS acc[4][2][kK3Park][kMaxAngles];      // per group, bank, parking slot and direction: finished tiles wait
+                                                // here until kK3Park of them get their epilogues at once, one per
+                                                // lane, while the next batch already fills the other bank
     int box[4][2][4];                           // mask bounding box per group and tile parity: rmin rmax cmin cmax
     uint32_t wmax[4][32];                       // per-warp maxima (only when K1 did not run)
     K3TileInfo info[4][2];                      // per group and tile parity
-    uint32_t tileid[4][2][2];                   // output row and channel slot of the tile whose epilogue is still due
+    uint32_t tileid[4][2][kK3Park][2];          // output row and channel slot of the parked tiles
 };
 struct K3Group {                               // where the quantised tile and its mask bits live
     uint32_t* q8;                              // quantised pixels (bytes) + slack for unaligned reads
@@ -324,7 +326,8 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
     const int id_sync = 1 + g, id_mine = 1 + NG + g, id_next = 1 + NG + (g + 1) % NG;
 
     for (int k = tid; k < 32768; k += kK3Threads) S.hist[k] = 0u;
-    if (tid < 4 * 2 * kMaxAngles * (int)(sizeof(K3AccS) / 4)) reinterpret_cast<uint32_t*>(&S.acc[0][0][0])[tid] = 0u;
+    for (int k = tid; k < 4 * 2 * kK3Park * kMaxAngles * (int)(sizeof(K3AccS) / 4); k += kK3Threads)
+        reinterpret_cast<uint32_t*>(&S.acc[0][0][0][0])[k] = 0u;
     if (tid < 256) S.homtab[tid] = 1.0 / (1.0 + (double)(tid * tid));
     if (tid < 8) { S.box[tid >> 1][tid & 1][0] = 1 << 30; S.box[tid >> 1][tid & 1][1] = -1; S.box[tid >> 1][tid & 1][2] = 1 << 30; S.box[tid >> 1][tid & 1][3] = -1; }
     __syncthreads();
@@ -371,21 +374,24 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
         if (!fast) k3_magic(vmax, mul, sh);
         I.mul = mul; I.sh = sh; I.fast = fast ? 1u : 0u;
     };
-    // The epilogue of a tile (FP64 divisions and square roots, one lane per direction): lane 0 of the last
-    // warps, one direction each.
-    auto epilogue_of = [&](int eb) {
-        const int d = gwarps - 1 - gw;
-        if (d < P.n_angles && lane == 0) {
-            const uint32_t row = S.tileid[g][eb][0];
-            K3AccS& Acc = S.acc[g][eb][d];
+    // Epilogues (FP64 divisions and square roots, ~150 instructions per tile and direction) are parked: a
+    // tile's sums stay in its parking slot, and once kK3Park tiles are parked the last warp of the group
+    // finishes all of them at once, one (tile, direction) per lane.
+    auto run_epilogues = [&](int bank, int count) {        // last warp of the group
+        const int slot = lane / kMaxAngles, d = lane % kMaxAngles;
+        if (gw == gwarps - 1 && slot < count && d < P.n_angles) {
+            const uint32_t row = S.tileid[g][bank][slot][0];
+            K3AccS& Acc = S.acc[g][bank][slot][d];
             k3_epilogue(P, P.out + (long long)row * P.row_stride, P.status ? P.status + row : nullptr,
-                        (int)S.tileid[g][eb][1], d, Acc);
+                        (int)S.tileid[g][bank][slot][1], d, Acc);
 #pragma unroll
             for (int k = 0; k < 8; ++k) Acc.s[k] = 0u;
             Acc.hom_lo = 0u; Acc.hom_hi = 0u;
             Acc.np = 0u;
         }
     };
+    static_assert(kK3Park * kMaxAngles <= 32, "one lane per parked (tile, direction)");
+    int parked = 0, pbank = 0;                             // parking slot and bank of the current tile
     if (scout && my_count) resolve(t, 0);
     bar_sync(id_sync, gthreads);
     if (my_count) start_copies(0);
@@ -401,7 +407,7 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
         if (active) {
             const K3TileInfo& I = S.info[g][buf];
             tw = I.w; th = I.h;
-            if (gt == 0) { S.tileid[g][buf][0] = I.row; S.tileid[g][buf][1] = I.slot; }
+            if (gt == 0) { S.tileid[g][pbank][parked][0] = I.row; S.tileid[g][pbank][parked][1] = I.slot; }
             const int tn = th * tw;
             // pixels and mask bytes: from the prefetch buffer, or straight from global memory
             const uint16_t* pxs = reinterpret_cast<const uint16_t*>(raw);
@@ -522,7 +528,7 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
             uint32_t hit[kCache][16];
             uint32_t sold = 0u, valid = 0u, np = 0u;
             K3Acc A = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0.0};
-            K3AccS& Acc = S.acc[g][buf][a];
+            K3AccS& Acc = S.acc[g][pbank][parked][a];
             auto sums16 = [&](const uint32_t (&I4)[4], const uint32_t (&J4)[4], uint32_t pm) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) k3_sums(S.homtab, I4[k], J4[k], k3_expand4(pm >> (4 * k)), A);
@@ -615,11 +621,12 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, int prefetch) {
         cp_async_wait_all();
         if (scout && j + 1 < my_count) publish(buf ^ 1);
         bar_sync(id_sync, gthreads);                       // sums final, staging buffers free, next tile prepared
-        if (active) epilogue_of(buf);                      // on the last warps: the scout's warp aside, the least loaded
+        if (active && ++parked == kK3Park) { run_epilogues(pbank, kK3Park); parked = 0; pbank ^= 1; }
         if (MASKED && active && gt == 0) {
             S.box[g][buf][0] = 1 << 30; S.box[g][buf][1] = -1; S.box[g][buf][2] = 1 << 30; S.box[g][buf][3] = -1;
         }
     }
+    run_epilogues(pbank, parked);
 }
 
 }  // namespace imfeat
