@@ -17,7 +17,8 @@
 // * each group stages its own tile (maximum from K1's column when the basic block ran, mask bits and
 //   their bounding box, 8-bit quantisation into shared memory) while other groups use the table.  The
 //   raw pixels and mask bytes of a group's next tile are prefetched into shared memory with cp.async
-//   while it works on the current one, so staging never waits for global memory.
+//   while it works on the current one, so staging never waits for global memory.  Per-tile scalar work
+//   sits on one lane of the last warp; the epilogues of 8 parked tiles run at once on that warp.
 // * ASM = sum_bins c^2 is accumulated from the atomics' return values
 //   (c^2 = sum_{k<c} (2k+1) = 2*sum(old) + c), so there is no pass over the bins.
 #pragma once
