@@ -315,7 +315,7 @@ def run_b200(args):
                      "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
                      "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read+write per launch)" if traffic else None,
                      "algorithmic_bytes": n_obj * algorithmic_bytes_per_object(HS, WS, C, 1, feats[names.index(dom["kernel"])]),
-                     "bound_note": "HBM is the roofline asked for; ncu shows this kernel limited by the shared-memory pipe and instruction issue (57% / 56% busy, group barriers the top stall), see profiles/",
+                     "bound_note": "HBM is the roofline asked for; ncu shows this kernel limited by the shared-memory pipe and instruction issue (about 60% busy each, group barriers the top stall), see profiles/",
                      "note": "algorithmic bytes = N*(2hwC + 1*hwC + 8*F_k*C), F_k = this kernel's features"},
         "roofline_kernels": per_kernel,
         "roofline_path": {"achieved": b_path / (ms_step * 1e-3) / 1e9, "frac": b_path / (ms_step * 1e-3) / 1e9 / peak},
