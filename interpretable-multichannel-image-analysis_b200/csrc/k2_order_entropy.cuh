@@ -445,16 +445,18 @@ __global__ void __launch_bounds__(kK2cThreads, 24) k2c_order_entropy_kernel(cons
         const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
         const int nfull = T.n >> 3, rem = T.n & 7;
         uint32_t cnt = 0;
-        // software pipeline: the next chunk's loads are in flight while this one goes into the histogram
-        uint4 vn = make_uint4(0u, 0u, 0u, 0u);
-        uint2 mn = make_uint2(0u, 0u);
+        // software pipeline: the loads of the next two chunks are in flight while this one goes into the histogram
+        uint4 vn = make_uint4(0u, 0u, 0u, 0u), vn2 = vn;
+        uint2 mn = make_uint2(0u, 0u), mn2 = mn;
         if (tid < nfull) { vn = ld_stream(px4 + tid); if (MASKED) mn = __ldg(mk2 + tid); }
+        if (tid + kK2cThreads < nfull) { vn2 = ld_stream(px4 + tid + kK2cThreads); if (MASKED) mn2 = __ldg(mk2 + tid + kK2cThreads); }
         for (int idx = tid; idx < nfull; idx += kK2cThreads) {
             const uint4 v = vn;
             const uint2 m = mn;
-            if (idx + kK2cThreads < nfull) {
-                vn = ld_stream(px4 + idx + kK2cThreads);
-                if (MASKED) mn = __ldg(mk2 + idx + kK2cThreads);
+            vn = vn2; mn = mn2;
+            if (idx + 2 * kK2cThreads < nfull) {
+                vn2 = ld_stream(px4 + idx + 2 * kK2cThreads);
+                if (MASKED) mn2 = __ldg(mk2 + idx + 2 * kK2cThreads);
             }
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
             const uint32_t nz[2] = {__vcmpne4(m.x, 0u), __vcmpne4(m.y, 0u)};      // 0xff per pixel inside the mask
