@@ -420,13 +420,23 @@ __global__ void __launch_bounds__(kK2cThreads, 24) k2c_order_entropy_kernel(cons
     __syncthreads();
 
     static_assert(kK2cThreads == 32, "the dynamic scheduler below assumes one warp per CTA");
+    // min and max of a tile (written by K1, earlier launch on the same stream), fetched one tile ahead
+    auto peek = [&](long long tt, double& a, double& b) {
+        if (tt >= P.n_tiles) return;
+        const uint32_t row = (uint32_t)tt / (uint32_t)P.c_out, slot = (uint32_t)tt - row * (uint32_t)P.c_out;
+        const double* q = P.out + (long long)row * P.row_stride + P.col_basic + kNBasic * (int)slot;
+        a = q[0]; b = q[10];
+    };
     long long tnext = next_tile(P.sched + 1);
+    double dmin_n = 0.0, dmax_n = 0.0;
+    peek(tnext, dmin_n, dmax_n);
     while (tnext < P.n_tiles) {
         const long long t = tnext;
+        const double dmin = dmin_n, dmax = dmax_n;
         tnext = next_tile(P.sched + 1);                      // one tile ahead
+        peek(tnext, dmin_n, dmax_n);
         const Tile T = resolve_tile(P, t);
         double* o = T.out_row + P.col_basic + kNBasic * T.slot;
-        const double dmin = o[0], dmax = o[10];              // written by K1 (earlier launch, same stream)
         if (!(dmin == dmin)) {                               // NaN: no pixel inside the mask
             if (tid == 0) {
                 const double nan = qnan();
