@@ -5,8 +5,9 @@
 //
 // Single pass over HBM.  min / max / sum use packed 16-bit SIMD (2 pixels per instruction).  The
 // central moments are accumulated around an integer pivot p taken from a small sample of the
-// tile (the mean of ~256 valid pixels), y = x - p: as exact 64-bit integers (IMAD.WIDE) while
-// |y| <= 11,585 -- all 12-bit data -- and otherwise, in a second pass over the tile, as doubles
+// tile (the mean of ~256 valid pixels spread over it), y = x - p: as exact 64-bit integers (IMAD.WIDE)
+// while |y| <= 11,585 -- all 12-bit data -- and otherwise (sample range too wide, or the limit found
+// broken after the pass) as doubles
 // (y formed exactly by an integer add into the mantissa of 2^52, then sum y^2 (exact), y^3, y^4
 // with FP64 FMAs).
 // The pivot is shifted to the exact mean analytically in the epilogue; because the pivot is the
@@ -219,25 +220,32 @@ __global__ void __launch_bounds__(256) k1_moments_kernel(const __grid_constant__
             tail_ok = !MASKED || T.mk[nfull * 8 + lane] != 0;
         }
         uint32_t ssum = tail_ok ? xt : 0u, scnt = tail_ok ? 1u : 0u;
+        uint32_t smn2 = 0xffffffffu, smx2 = 0u;            // extremes of the sample (packed 16-bit pairs)
         {
-            const int s0 = nfull > 32 ? (nfull >> 1) - 16 : 0;
-            const int idx = s0 + lane;
+            // 32 vectors spread evenly over the tile: the pivot (their mean) and a first idea of the range
+            // (stride + 1/2: a stride that is a multiple of the row length would sample one column only)
+            const int stride = nfull >> 5;
+            const int idx = nfull <= 32 ? lane : min((lane * (2 * stride + 1)) >> 1, nfull - 1);
             if (idx < nfull) {
                 uint4 v = ld_reuse(px4 + idx);
+                uint32_t h0 = 0xffffffffu, h1 = h0, h2 = h0, h3 = h0;
                 if (MASKED) {
                     const uint2 m = __ldg(mk2 + idx);
-                    uint32_t h0, h1, h2, h3;
                     mask_halfwords(m.x, h0, h1);
                     mask_halfwords(m.y, h2, h3);
-                    v.x &= h0; v.y &= h1; v.z &= h2; v.w &= h3;
                     scnt += (__popc(h0) + __popc(h1) + __popc(h2) + __popc(h3)) >> 4;
                 } else {
                     scnt += 8;
                 }
+                smn2 = __vminu2(__vminu2(v.x | ~h0, v.y | ~h1), __vminu2(v.z | ~h2, v.w | ~h3));
+                v.x &= h0; v.y &= h1; v.z &= h2; v.w &= h3;
+                smx2 = __vmaxu2(__vmaxu2(v.x, v.y), __vmaxu2(v.z, v.w));
                 ssum = __dp2a_lo(v.x, 0x0101u, ssum); ssum = __dp2a_lo(v.y, 0x0101u, ssum);
                 ssum = __dp2a_lo(v.z, 0x0101u, ssum); ssum = __dp2a_lo(v.w, 0x0101u, ssum);
             }
         }
+        const uint32_t smin = __reduce_min_sync(0xffffffffu, min(smn2 & 0xffffu, smn2 >> 16));
+        const uint32_t smax = __reduce_max_sync(0xffffffffu, max(smx2 & 0xffffu, smx2 >> 16));
         ssum = __reduce_add_sync(0xffffffffu, ssum);
         scnt = __reduce_add_sync(0xffffffffu, scnt);
         if (MASKED && scnt == 0 && nfull > 0) {
@@ -261,7 +269,10 @@ __global__ void __launch_bounds__(256) k1_moments_kernel(const __grid_constant__
 
         // ---- the streaming pass: exact integer sums first (see K1IntState) ----
         bool done = false;
-        if (!P.k1_fp64_only) {
+        // the sample already shows a range beyond the integer limit: go straight to the FP64 pass
+        const bool sample_wide = scnt != 0u && smin <= smax &&
+                                 ((int)smax - (int)p > kK1IntLimit || (int)p - (int)smin > kK1IntLimit);
+        if (!P.k1_fp64_only && !sample_wide) {
             K1IntState st;
             st.mn2 = 0xffffffffu; st.mx2 = 0u; st.sum = 0u; st.cnt = 0u;
             st.S2 = 0ull; st.S3[0] = 0; st.S3[1] = 0; st.S4[0] = 0ull; st.S4[1] = 0ull;
