@@ -70,6 +70,8 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(imf.ImfeatError):
         imf.extract_features(np.zeros((1, 8, 8, 2), np.uint16))
+    with pytest.raises(imf.ImfeatError):
+        imf.MinMaxScaler().fit(np.zeros((4, 3)))
 
 
 def test_product_does_not_import_the_oracle():
