@@ -9,12 +9,12 @@ from . import ablation, batcher, distributed, postprocess, schema, synth
 from .batcher import PinnedBatcher
 from .postprocess import MinMaxScaler
 from ._lib import ImfeatError
-from .extractor import (FeatureExtractor, basic_statistical_features, extract_features,
+from .extractor import (FeatureExtractor, basic_statistical_features, extract_features, from_unit_float,
                         get_extractor, glcm_features, plane_stride_for)
 from .schema import feature_columns
 
 __all__ = [
     "FeatureExtractor", "ImfeatError", "basic_statistical_features", "extract_features",
-    "feature_columns", "get_extractor", "glcm_features", "plane_stride_for", "schema",
+    "feature_columns", "from_unit_float", "get_extractor", "glcm_features", "plane_stride_for", "schema",
     "ablation", "batcher", "distributed", "postprocess", "synth", "PinnedBatcher", "MinMaxScaler",
 ]

@@ -79,10 +79,13 @@ class CapturedSweep:
     re-extractions (5 kernels each) on the current contents of ``planes`` / ``masks`` with a single
     launch and no host work in between -- e.g. once per bootstrap replicate or per augmented copy
     written into the same buffers.  The index tensors, the output block and the extractor's internal
-    buffers are fixed at capture time; per-kernel timing must be off while capturing."""
+    buffers are fixed at capture time, so the sweep works on a private clone of the extractor (its own
+    context: later, larger batches through the original extractor can neither move nor share the work
+    buffers and scheduler counters whose addresses the graph holds)."""
 
     def __init__(self, extractor, planes, masks=None, sizes=None, hs=None, ws=None, mode="loco", seed=42):
         import torch
+        extractor = extractor.clone()
         self.extractor, self.planes, self.masks = extractor, planes, masks
         self.index = sweep_index(planes, mode, seed)
         kw = dict(sizes=sizes, hs=hs, ws=ws, mode=mode, seed=seed, index=self.index)

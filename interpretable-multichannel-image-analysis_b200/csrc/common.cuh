@@ -210,6 +210,17 @@ __device__ __forceinline__ unsigned long long warp_sum_redux(unsigned long long 
     return s0 + (s1 << 21) + (s2 << 42);
 }
 
+// The same three limb sums combined in floating point: the total of 32 lanes may exceed 64 bits even though
+// every lane's value fits (K1's sum of fourth powers: 1,024 * y^4 < 2^64 per lane, times 32 lanes).
+__device__ __forceinline__ double warp_sum_redux_dbl(unsigned long long v) {
+    const uint32_t l0 = (uint32_t)v & 0x1fffffu, l1 = (uint32_t)(v >> 21) & 0x1fffffu;
+    const uint32_t l2 = (uint32_t)(v >> 42);
+    const uint32_t s0 = __reduce_add_sync(0xffffffffu, l0);         // 32 * 2^21 and 32 * 2^22 fit 32 bits
+    const uint32_t s1 = __reduce_add_sync(0xffffffffu, l1);
+    const uint32_t s2 = __reduce_add_sync(0xffffffffu, l2);
+    return (double)s0 + (double)s1 * 2097152.0 + (double)s2 * 4398046511104.0;
+}
+
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
 }  // namespace imfeat

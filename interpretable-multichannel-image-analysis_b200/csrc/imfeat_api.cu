@@ -13,6 +13,7 @@
 #include "k1_moments.cuh"
 #include "k2_order_entropy.cuh"
 #include "k3_glcm.cuh"
+#include "k3_ring.cuh"
 #include "k4_shape.cuh"
 
 using namespace imfeat;
@@ -34,6 +35,12 @@ struct imfeat_ctx {
     uint32_t* d_worklist;       // [0] = count, [1..] = tile ids left to the full-range K2 kernel
     size_t worklist_cap;        // entries per ring slot
     unsigned int wl_head;
+    void* retired[64];          // outgrown work buffers: kept until imfeat_destroy (a captured graph or a call in
+    int n_retired;              // flight on another stream may still hold their addresses)
+    // K3 scratch (quantised tiles between the front and the bins kernel): two slots, handed out in turn; a slot
+    // is reused only after the event recorded behind its last consumer
+    struct { unsigned char* ptr; size_t bytes; cudaEvent_t ev; int recorded; } scr[2];
+    unsigned int scr_head;
     double* d_log2tab;
     unsigned long long* d_gfix;
     long long launches;
@@ -48,7 +55,7 @@ struct imfeat_ctx {
     size_t in_bytes, out_bytes;
     // optional per-kernel timing (imfeat_enable_timing): a ring of event sets, resolved lazily
     // debugging / measurement switches, read from the environment once at imfeat_create
-    int env_k1_fp64, env_k1_tma, env_k2_compact, env_k4_warp, env_k2_groups;
+    int env_k1_fp64, env_k1_tma, env_k2_compact, env_k4_warp, env_k2_groups, env_k3_threads, env_k3_chunk, env_k3_ring;
     int timing;
     int t_head, t_pending;
     cudaEvent_t t_ev[kTimingSlots][5];
@@ -67,6 +74,20 @@ static int fail(imfeat_ctx* ctx, int code, const char* fmt, ...) {
     if (ctx) memcpy(ctx->err, g_err, sizeof(g_err));
     return code;
 }
+
+// Every entry point works on the context's device and puts the caller's current device back on return
+// (PyTorch reads the current device through cudaGetDevice: leaving it changed would silently move the
+// calling thread's later allocations, streams and NCCL calls to another GPU).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 #define CU(call)                                                                          \
     do {                                                                                  \
@@ -112,7 +133,7 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
     CU(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count)
         return fail(nullptr, IMFEAT_ERR_ARG, "device %d out of range (%d CUDA devices)", device, count);
-    CU(cudaSetDevice(device));
+    DeviceGuard guard(device);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
@@ -130,6 +151,10 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
         ctx->env_k4_warp = flag("IMFEAT_K4_WARP", 1);       // 0: CTA-per-tile K4 for every batch
         const int g2 = flag("IMFEAT_K2_GROUPS", 4);
         ctx->env_k2_groups = (g2 == 2 || g2 == 4 || g2 == 8) ? g2 : 4;
+        ctx->env_k3_threads = flag("IMFEAT_K3_THREADS", 128) == 256 ? 256 : 128;   // threads per K3 CTA
+        ctx->env_k3_chunk = flag("IMFEAT_K3_CHUNK", 16384);                        // objects per front/bins round of K3
+        if (ctx->env_k3_chunk < 1) ctx->env_k3_chunk = 16384;
+        ctx->env_k3_ring = flag("IMFEAT_K3_RING", 1);       // 1: unmasked tiles through the one-kernel ring variant (k3_ring.cuh)
     }
     ctx->sm_count = prop.multiProcessorCount;
     // log2 table, computed on the host in double precision (k = 0 maps to 0, never used)
@@ -156,14 +181,18 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
     free(tab);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_order_entropy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_order_entropy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ring::k3_glcm_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ring::k3_glcm_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3a_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3a_front_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k4_shape_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k4_shape_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_moments_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -199,7 +228,7 @@ static void free_staging(imfeat_ctx* ctx) {
 
 int imfeat_destroy(imfeat_ctx* ctx) {
     if (!ctx) return IMFEAT_OK;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     free_staging(ctx);
     for (int b = 0; b < 2; ++b) {
         if (ctx->streams[b]) cudaStreamDestroy(ctx->streams[b]);
@@ -211,6 +240,11 @@ int imfeat_destroy(imfeat_ctx* ctx) {
     if (ctx->d_log2tab) cudaFree(ctx->d_log2tab);
     if (ctx->d_gfix) cudaFree(ctx->d_gfix);
     if (ctx->d_worklist) cudaFree(ctx->d_worklist);
+    for (int k = 0; k < ctx->n_retired; ++k) cudaFree(ctx->retired[k]);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->scr[k].ptr) cudaFree(ctx->scr[k].ptr);
+        if (ctx->scr[k].ev) cudaEventDestroy(ctx->scr[k].ev);
+    }
     if (ctx->d_sched) cudaFree(ctx->d_sched);
     free(ctx);
     return IMFEAT_OK;
@@ -218,15 +252,84 @@ int imfeat_destroy(imfeat_ctx* ctx) {
 
 }  // extern "C"
 
-template <bool DUMP>
-static void launch_k3(bool masked, int ng, int grid, size_t smem, cudaStream_t st, const Params& P, int maxpx) {
-    if (ng == 4) {
-        if (masked) k3_glcm_kernel<true, DUMP, 4><<<grid, kK3Threads, smem, st>>>(P, maxpx, k3_prefetch(maxpx, masked) ? 1 : 0);
-        else k3_glcm_kernel<false, DUMP, 4><<<grid, kK3Threads, smem, st>>>(P, maxpx, k3_prefetch(maxpx, masked) ? 1 : 0);
-    } else {
-        if (masked) k3_glcm_kernel<true, DUMP, 2><<<grid, kK3Threads, smem, st>>>(P, maxpx, k3_prefetch(maxpx, masked) ? 1 : 0);
-        else k3_glcm_kernel<false, DUMP, 2><<<grid, kK3Threads, smem, st>>>(P, maxpx, k3_prefetch(maxpx, masked) ? 1 : 0);
+// A work buffer that must grow is never freed or reused in place: a captured CUDA graph (ablation.CapturedSweep)
+// or a call in flight on another stream may hold its address.  It is retired until imfeat_destroy; and nothing
+// can be allocated while the stream is being captured.
+static int grow_buffer(imfeat_ctx* ctx, cudaStream_t st, void** buf, size_t bytes, const char* what) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CU(cudaStreamIsCapturing(st, &cap));
+    if (cap != cudaStreamCaptureStatusNone)
+        return fail(ctx, IMFEAT_ERR_ARG, "the batch outgrew the context's %s during stream capture; run one eager call "
+                    "of this size first", what);
+    if (*buf) {
+        if (ctx->n_retired == 64) return fail(ctx, IMFEAT_ERR_NOMEM, "too many work-buffer generations");
+        ctx->retired[ctx->n_retired++] = *buf;
+        *buf = nullptr;
     }
+    CU(cudaMalloc(buf, bytes));
+    return IMFEAT_OK;
+}
+
+// K3 = front kernel (one warp per tile: quantised tile + geometry into the scratch record, pair sums into the
+// output records), bins kernel (persistent CTAs of NT threads, as many as fit an SM: three for 64x64 tiles),
+// finalize kernel (raw sums -> the six properties).  Front and bins alternate over chunks of objects so that the
+// scratch records of a chunk are still in L2 when the bins kernel fetches them.
+template <bool DUMP, int NT>
+static int launch_k3_nt(imfeat_ctx* ctx, bool masked, cudaStream_t st, const Params& P, int maxpx) {
+    const size_t rec = k3_rec_bytes(maxpx, masked);
+    const size_t smem_b = k3_smem_bytes(maxpx, masked), smem_a = (size_t)kK3aWarps * k3a_warp_bytes(maxpx, masked);
+    int bps_a = 0, bps_b = 0;
+    cudaError_t e = masked ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_b, k3_glcm_kernel<true, DUMP, NT>, NT, smem_b)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_b, k3_glcm_kernel<false, DUMP, NT>, NT, smem_b);
+    if (e == cudaSuccess)
+        e = masked ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_a, k3a_front_kernel<true>, 32 * kK3aWarps, smem_a)
+                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_a, k3a_front_kernel<false>, 32 * kK3aWarps, smem_a);
+    if (e != cudaSuccess) return fail(ctx, IMFEAT_ERR_CUDA, "K3 occupancy query failed: %s", cudaGetErrorString(e));
+    if (bps_a < 1 || bps_b < 1) return fail(ctx, IMFEAT_ERR_CUDA, "K3 does not fit an SM (%zu / %zu bytes of shared memory)", smem_a, smem_b);
+    // chunks of whole objects, evenly sized
+    const long long chunk_tiles = (long long)ctx->env_k3_chunk * P.c_out;
+    const long long n_chunks = (P.n_tiles + chunk_tiles - 1) / chunk_tiles;
+    const long long per = (P.n_tiles + n_chunks - 1) / n_chunks;
+    // scratch slot: wait for its last consumer (possibly on another stream), grow if needed
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CU(cudaStreamIsCapturing(st, &cap));
+    auto& slot = ctx->scr[ctx->scr_head++ & 1u];
+    if (cap == cudaStreamCaptureStatusNone && slot.recorded) CU(cudaStreamWaitEvent(st, slot.ev, 0));
+    if (slot.bytes < (size_t)per * rec) {
+        if (cap == cudaStreamCaptureStatusNone && slot.recorded) CU(cudaEventSynchronize(slot.ev));
+        int rc = grow_buffer(ctx, st, (void**)&slot.ptr, (size_t)per * rec, "K3 scratch");
+        if (rc) { slot.bytes = 0; return rc; }
+        slot.bytes = (size_t)per * rec;
+    }
+    for (long long c = 0; c < n_chunks; ++c) {
+        const long long t0 = c * per;
+        const uint32_t nl = (uint32_t)(P.n_tiles - t0 < per ? P.n_tiles - t0 : per);
+        CU(cudaMemsetAsync(P.sched + 5, 0, 2 * sizeof(unsigned int), st));     // the tile counters of the two kernels
+        const long long warps_a = (long long)ctx->sm_count * bps_a * kK3aWarps;
+        const int grid_a = (int)((nl < warps_a ? nl : warps_a) + kK3aWarps - 1) / kK3aWarps;
+        if (masked) k3a_front_kernel<true><<<grid_a, 32 * kK3aWarps, smem_a, st>>>(P, maxpx, (uint32_t)t0, nl, slot.ptr);
+        else k3a_front_kernel<false><<<grid_a, 32 * kK3aWarps, smem_a, st>>>(P, maxpx, (uint32_t)t0, nl, slot.ptr);
+        const long long res_b = (long long)ctx->sm_count * bps_b;
+        const int grid_b = (int)(nl < res_b ? nl : res_b);
+        if (masked) k3_glcm_kernel<true, DUMP, NT><<<grid_b, NT, smem_b, st>>>(P, maxpx, nl, slot.ptr);
+        else k3_glcm_kernel<false, DUMP, NT><<<grid_b, NT, smem_b, st>>>(P, maxpx, nl, slot.ptr);
+        ctx->launches += 2;
+    }
+    const long long recs = P.n_tiles * P.n_angles;
+    const long long want = (recs + 255) / 256, capg = 8ll * ctx->sm_count;
+    k3_finalize_kernel<<<(int)(want < capg ? want : capg), 256, 0, st>>>(P);
+    ctx->launches += 1;
+    if (cap == cudaStreamCaptureStatusNone) {
+        if (!slot.ev) CU(cudaEventCreateWithFlags(&slot.ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(slot.ev, st));
+        slot.recorded = 1;
+    }
+    return IMFEAT_OK;
+}
+template <bool DUMP>
+static int launch_k3(imfeat_ctx* ctx, bool masked, cudaStream_t st, const Params& P, int maxpx) {
+    return ctx->env_k3_threads == 128 ? launch_k3_nt<DUMP, 128>(ctx, masked, st, P, maxpx)
+                                      : launch_k3_nt<DUMP, 256>(ctx, masked, st, P, maxpx);
 }
 
 // K2: measured on B200 (10,000 64x64x12 objects): unmasked 1.59 ms with 4 groups vs 1.84 ms with 2;
@@ -237,7 +340,7 @@ static int k2_groups(const imfeat_ctx* ctx) { return ctx->env_k2_groups; }
 static int c_round(double v) { return (int)(v < 0 ? -floor(-v + 0.5) : floor(v + 0.5)); }
 
 static int check_common(imfeat_ctx* ctx, const void* planes, int64_t n, int c_in, int c_out, int hs,
-                        int ws, int64_t plane_stride, const imfeat_opts* o) {
+                        int ws, int64_t plane_stride, const imfeat_opts* o, bool device_ptr = true) {
     if (!ctx) return fail(nullptr, IMFEAT_ERR_ARG, "ctx is NULL");
     if (!o || o->struct_size != (int32_t)sizeof(imfeat_opts))
         return fail(ctx, IMFEAT_ERR_ARG, "opts is NULL or has the wrong struct_size");
@@ -250,7 +353,8 @@ static int check_common(imfeat_ctx* ctx, const void* planes, int64_t n, int c_in
         return fail(ctx, IMFEAT_ERR_ARG, "object size %dx%d outside 1..%d pixels per plane", hs, ws, kMaxPixels);
     if (plane_stride < (int64_t)hs * ws || (plane_stride & 7))
         return fail(ctx, IMFEAT_ERR_ARG, "plane_stride must be >= hs*ws and a multiple of 8");
-    if (((uintptr_t)planes & 15) != 0) return fail(ctx, IMFEAT_ERR_ARG, "planes must be 16-byte aligned");
+    // only device planes are read with 128-bit loads; host buffers are copied (memcpy / DMA) first
+    if (device_ptr && ((uintptr_t)planes & 15) != 0) return fail(ctx, IMFEAT_ERR_ARG, "planes must be 16-byte aligned");
     if (o->want_glcm && (o->n_angles < 1 || o->n_angles > kMaxAngles))
         return fail(ctx, IMFEAT_ERR_ARG, "n_angles must be 1..%d", kMaxAngles);
     if (o->want_glcm && (o->glcm_distance < 1 || o->glcm_distance > 255))
@@ -363,13 +467,13 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
             // remaining tiles to a worklist that the full-range ring kernel then works off
             // the worklist lives in a ring of kWlSlots buffers: calls on different streams (e.g. the two
             // streams of the host pipeline) may be in flight at the same time
-            if ((size_t)P.n_tiles + 1 > ctx->worklist_cap) {
-                CU(cudaDeviceSynchronize());               // rare: the batch grew; nobody may still use the old buffers
-                if (ctx->d_worklist) CU(cudaFree(ctx->d_worklist));
-                ctx->d_worklist = nullptr;
+            if ((size_t)P.n_tiles + 1 > ctx->worklist_cap) {             // rare: the batch grew
+                size_t cap_new = (size_t)P.n_tiles + 1;
+                if (cap_new < 2 * ctx->worklist_cap) cap_new = 2 * ctx->worklist_cap;
                 ctx->worklist_cap = 0;
-                CU(cudaMalloc((void**)&ctx->d_worklist, sizeof(uint32_t) * kWlSlots * ((size_t)P.n_tiles + 1)));
-                ctx->worklist_cap = (size_t)P.n_tiles + 1;
+                int rcw = grow_buffer(ctx, st, (void**)&ctx->d_worklist, sizeof(uint32_t) * kWlSlots * cap_new, "worklist");
+                if (rcw) return rcw;
+                ctx->worklist_cap = cap_new;
             }
             uint32_t* wl = ctx->d_worklist + (size_t)(ctx->wl_head++ % kWlSlots) * ctx->worklist_cap;
             CU(cudaMemsetAsync(wl, 0, sizeof(uint32_t), st));
@@ -405,11 +509,21 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
         ctx->launches += 1;
     }
     if (o->want_glcm) {
-        const int g3 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
         const int maxpx = ((P.hs * P.ws + 7) & ~7);
-        launch_k3<false>(masked, k3_groups(maxpx, masked), g3, k3_smem_bytes(maxpx, masked), st, P, maxpx);
+        if (!masked && ctx->env_k3_ring) {
+            // unmasked tiles: the one-kernel ring variant is the faster one (see k3_ring.cuh)
+            const int g3 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
+            const int ng = ring::k3_groups(maxpx, false);
+            const size_t smem3 = ring::k3_smem_bytes(maxpx, false);
+            const int pf = ring::k3_prefetch(maxpx, false) ? 1 : 0;
+            if (ng == 4) ring::k3_glcm_kernel<false, false, 4><<<g3, ring::kK3Threads, smem3, st>>>(P, maxpx, pf);
+            else ring::k3_glcm_kernel<false, false, 2><<<g3, ring::kK3Threads, smem3, st>>>(P, maxpx, pf);
+            ctx->launches += 1;
+        } else {
+            int rc3 = launch_k3<false>(ctx, masked, st, P, maxpx);
+            if (rc3) return rc3;
+        }
         IMFEAT_MARK(2)
-        ctx->launches += 1;
     }
 #undef IMFEAT_MARK
     CU(cudaGetLastError());
@@ -423,7 +537,7 @@ int imfeat_minmax_fit_device(imfeat_ctx* ctx, const double* d_table, int64_t n_r
     if (!ctx) return fail(nullptr, IMFEAT_ERR_ARG, "ctx is NULL");
     if (n_rows < 0 || n_cols <= 0 || row_stride < n_cols) return fail(ctx, IMFEAT_ERR_ARG, "bad table shape");
     if (!d_stats || (n_rows > 0 && !d_table)) return fail(ctx, IMFEAT_ERR_ARG, "NULL table or stats pointer");
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int blocks = (int)(n_rows < kPostRowBlocks ? (n_rows > 0 ? n_rows : 1) : kPostRowBlocks);
     double* partial = nullptr;
@@ -445,7 +559,7 @@ int imfeat_minmax_transform_device(imfeat_ctx* ctx, const double* d_in, int64_t 
         return fail(ctx, IMFEAT_ERR_ARG, "bad table shape");
     if (n_rows == 0) return IMFEAT_OK;
     if (!d_in || !d_out || !d_stats) return fail(ctx, IMFEAT_ERR_ARG, "NULL pointer");
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     const long long total = (long long)n_rows * n_cols;
     const long long want = (total + 255) / 256, cap = 8ll * ctx->sm_count;
@@ -464,7 +578,7 @@ int imfeat_enable_timing(imfeat_ctx* ctx, int32_t enable) {
 
 int imfeat_kernel_times(imfeat_ctx* ctx, double* ms_out, int64_t* calls_out, int32_t reset) {
     if (!ctx) return fail(nullptr, IMFEAT_ERR_ARG, "ctx is NULL");
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     for (int sl = 0; sl < kTimingSlots; ++sl) {
         int rc = timing_resolve(ctx, sl);
         if (rc) return rc;
@@ -492,7 +606,7 @@ int imfeat_extract_device(imfeat_ctx* ctx, const uint16_t* d_planes, const uint8
                     (long long)imfeat_row_width(c_out, opts));
     if (d_masks && ((uintptr_t)d_masks & 7)) return fail(ctx, IMFEAT_ERR_ARG, "masks must be 8-byte aligned");
     if (n_objects == 0) return IMFEAT_OK;
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (d_status) { CU(cudaMemsetAsync(d_status, 0, sizeof(uint32_t) * n_objects, st)); }
     Params P;
@@ -510,7 +624,7 @@ int imfeat_glcm_counts_device(imfeat_ctx* ctx, const uint16_t* d_planes, const u
     if (!opts->want_glcm) return fail(ctx, IMFEAT_ERR_ARG, "opts->want_glcm must be set");
     if (n_objects > 0 && !d_counts) return fail(ctx, IMFEAT_ERR_ARG, "d_counts is NULL");
     if (n_objects == 0) return IMFEAT_OK;
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     // the property columns are computed too; park them in a scratch table
     imfeat_opts o = *opts;
@@ -522,11 +636,13 @@ int imfeat_glcm_counts_device(imfeat_ctx* ctx, const uint16_t* d_planes, const u
     fill_params(P, ctx, d_planes, d_masks, d_sizes, nullptr, nullptr, n_objects, c, c, hs, ws,
                 plane_stride, &o, scratch, width, nullptr);
     P.counts = d_counts;
-    const int g3 = (int)(P.n_tiles < ctx->sm_count ? P.n_tiles : ctx->sm_count);
     const int maxpx = ((P.hs * P.ws + 7) & ~7);
     const bool masked = d_masks != nullptr;
-    launch_k3<true>(masked, k3_groups(maxpx, masked), g3, k3_smem_bytes(maxpx, masked), st, P, maxpx);
-    ctx->launches += 1;
+    // the tile counter of K3's dynamic scheduler (slot 2 of a work-counter set)
+    P.sched = ctx->d_sched + 8 * (ctx->sched_head++ % kSchedSlots);
+    CU(cudaMemsetAsync(P.sched, 0, sizeof(unsigned int) * 8, st));
+    rc = launch_k3<true>(ctx, masked, st, P, maxpx);
+    if (rc) return rc;
     CU(cudaGetLastError());
     CU(cudaFreeAsync(scratch, st));
     return IMFEAT_OK;
@@ -543,7 +659,7 @@ int imfeat_pack_hwc_device(imfeat_ctx* ctx, const uint16_t* d_hwc, const uint8_t
     if (!d_hwc || !d_planes) return fail(ctx, IMFEAT_ERR_ARG, "NULL image pointer");
     if ((d_mask_hwc == nullptr) != (d_masks == nullptr))
         return fail(ctx, IMFEAT_ERR_ARG, "mask input and output must both be given or both be NULL");
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     const long long total = (long long)n_objects * hs * ws;
     const long long want = (total + 255) / 256;
     const int grid = (int)(want < (long long)ctx->sm_count * 16 ? want : (long long)ctx->sm_count * 16);
@@ -565,7 +681,7 @@ int imfeat_synth_device(imfeat_ctx* ctx, uint64_t seed, int64_t first_object, in
         return fail(ctx, IMFEAT_ERR_ARG, "variable sizes need 1 <= hmin <= hs, 1 <= wmin <= ws and d_sizes");
     if (n_objects == 0) return IMFEAT_OK;
     if (!d_planes) return fail(ctx, IMFEAT_ERR_ARG, "d_planes is NULL");
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     const long long planes = (long long)n_objects * c;
     const int grid = (int)(planes < (long long)ctx->sm_count * 32 ? planes : (long long)ctx->sm_count * 32);
     synth_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, first_object, n_objects, c, hs, ws,
@@ -592,13 +708,19 @@ static int extract_host_impl(imfeat_ctx* ctx, int layout, const uint16_t* h_img,
                              const int32_t* h_sizes, int64_t n_objects, int32_t c, int32_t hs,
                              int32_t ws, int64_t plane_stride, const imfeat_opts* opts, double* h_out,
                              int64_t row_stride, uint32_t* h_status) {
-    int rc = check_common(ctx, h_img, n_objects, c, c, hs, ws, plane_stride, opts);
+    int rc = check_common(ctx, h_img, n_objects, c, c, hs, ws, plane_stride, opts, false);
     if (rc) return rc;
     if (n_objects > 0 && !h_out) return fail(ctx, IMFEAT_ERR_ARG, "h_out is NULL");
+    if (h_sizes)                                           // a size beyond the stride would read other objects' pixels
+        for (int64_t i = 0; i < n_objects; ++i) {
+            const int32_t h = h_sizes[2 * i], w = h_sizes[2 * i + 1];
+            if (h < 1 || w < 1 || h > hs || w > ws || (int64_t)h * w > plane_stride)
+                return fail(ctx, IMFEAT_ERR_ARG, "object %lld: size %dx%d outside 1..%dx%d", (long long)i, h, w, hs, ws);
+        }
     const int64_t width = imfeat_row_width(c, opts);
     if (row_stride < width) return fail(ctx, IMFEAT_ERR_ARG, "row_stride < row width");
     if (n_objects == 0) return IMFEAT_OK;
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     for (int b = 0; b < 2; ++b) {
         if (!ctx->streams[b]) CU(cudaStreamCreateWithFlags(&ctx->streams[b], cudaStreamNonBlocking));
         if (!ctx->done[b]) CU(cudaEventCreateWithFlags(&ctx->done[b], cudaEventDisableTiming));

@@ -314,8 +314,9 @@ __global__ void __launch_bounds__(256) k1_moments_kernel(const __grid_constant__
             if (n_eff == 0 || ((int)vmax - pi <= kK1IntLimit && pi - (int)vmin <= kK1IntLimit)) {
                 const unsigned long long S2 = warp_sum_redux(st.S2);
                 const long long S3 = (long long)warp_sum_redux((unsigned long long)(st.S3[0] + st.S3[1]));
-                const unsigned long long S4 = warp_sum_redux(st.S4[0] + st.S4[1]);
-                if (lane == 0) k1_park(pending + n_pending, P, T, n_eff, vmin, vmax, total, p, (double)S2, (double)S3, (double)S4);
+                // the lane sums fit 64 bits (see K1IntState), their total over the warp need not: combine in FP64
+                const double S4 = warp_sum_redux_dbl(st.S4[0] + st.S4[1]);
+                if (lane == 0) k1_park(pending + n_pending, P, T, n_eff, vmin, vmax, total, p, (double)S2, (double)S3, S4);
                 if (++n_pending == 32) { k1_flush(pending, 32, lane); n_pending = 0; }
                 done = true;
             }

@@ -81,6 +81,15 @@ class FeatureExtractor:
         _lib.check(self.lib.imfeat_create(int(self.device), ctypes.byref(self._ctx)))
 
     # -- bookkeeping -----------------------------------------------------------------------
+    def clone(self):
+        """A second extractor with the same options and its OWN context (work buffers, scheduler counters):
+        what a captured CUDA graph must use, because a graph bakes the context's buffer addresses in."""
+        o = self.opts
+        return FeatureExtractor(device=self.device, basic=bool(o.want_basic), glcm=bool(o.want_glcm),
+                                four_directions=o.n_angles == 4, shape=bool(o.want_shape),
+                                moments=bool(o.want_moments), percentiles=tuple(o.percentiles),
+                                distance=int(o.glcm_distance))
+
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx:
             self.lib.imfeat_destroy(self._ctx)
@@ -293,7 +302,29 @@ def _as_batch(images, masks):
     return batch, mb, sizes
 
 
-def extract_features(images, masks=None, channels=None, *, glcm=True, four_directions=False,
+def _as_uint16(batch):
+    """The reference's objects are 16-bit unsigned images (README.md:8).  Other integer types are accepted
+    when every value fits; floating-point input (the notebook's own demo feeds MedNIST JPEGs scaled to
+    [0, 1], NB:328) is refused rather than truncated: rescale it first, e.g. ``from_unit_float``."""
+    if batch.dtype == np.uint16:
+        return batch
+    if np.issubdtype(batch.dtype, np.integer) and (batch.size == 0 or (batch.min() >= 0 and batch.max() <= 65535)):
+        return batch.astype(np.uint16)
+    raise TypeError("images must be 16-bit unsigned integers (README.md:8), got %s" % batch.dtype)
+
+
+def from_unit_float(images, scale=255):
+    """Adapter for the notebook's demo data (NB:328, NB:360: ``add_two_noise_channels(im) / 255.``, float64
+    in [0, 1]): back to the integers they came from, ``rint(images * scale)`` as uint16.  Scale-free columns
+    (kurtosis, skew, entropy, all GLCM properties) are unchanged by the rescaling; intensity columns come
+    out in units of 1/scale."""
+    a = np.rint(np.asarray(images, dtype=np.float64) * scale)
+    if a.size and (a.min() < 0 or a.max() > 65535):
+        raise ValueError("scaled values leave the 16-bit range")
+    return a.astype(np.uint16)
+
+
+def extract_features(images, masks=None, channels=None, *, basic=True, glcm=True, four_directions=False,
                      shape=False, moments=False, percentiles=schema.NOTEBOOK_PERCENTILES,
                      distance=5, as_frame=False, device=None, return_status=False):
     """Drop-in for the notebook's extraction loop (NB:358-364).
@@ -307,11 +338,7 @@ def extract_features(images, masks=None, channels=None, *, glcm=True, four_direc
     the notebook's column names when ``as_frame`` is true).
     """
     batch, mb, sizes = _as_batch(images, masks)
-    if batch.dtype != np.uint16:
-        if np.issubdtype(batch.dtype, np.integer) and batch.size and batch.min() >= 0 and batch.max() <= 65535:
-            batch = batch.astype(np.uint16)
-        else:
-            raise TypeError("images must be 16-bit unsigned integers (README.md:8), got %s" % batch.dtype)
+    batch = _as_uint16(batch)
     if channels is not None and len(channels) and not isinstance(channels[0], str):
         sel = [int(c) for c in channels]
         batch = np.ascontiguousarray(batch[..., sel])
@@ -319,7 +346,7 @@ def extract_features(images, masks=None, channels=None, *, glcm=True, four_direc
             mb = np.ascontiguousarray(mb[..., sel])
     if mb is not None and mb.dtype != np.uint8:
         mb = (np.asarray(mb) != 0).astype(np.uint8)
-    ex = get_extractor(device, glcm=glcm, four_directions=four_directions, shape=shape,
+    ex = get_extractor(device, basic=basic, glcm=glcm, four_directions=four_directions, shape=shape,
                        moments=moments, percentiles=tuple(percentiles), distance=distance)
     res = ex.extract_host_hwc(batch, mb, sizes, return_status=return_status)
     table, status = res if return_status else (res, None)
@@ -333,15 +360,12 @@ def basic_statistical_features(image, device=None):
     """Same call and return shape as the reference function (NB:220-264): dict of 17 scalars
     per channel keyed ``<name>_Ch<k>``, for one (M, N, C) uint16 image."""
     image = np.asarray(image)
-    ex = get_extractor(device, glcm=False)
     row = extract_features(image[None], glcm=False, device=device)[0]
-    return dict(zip(ex.columns(image.shape[2]), (float(v) for v in row)))
+    return dict(zip(schema.feature_columns(image.shape[2], glcm=False), (float(v) for v in row)))
 
 
 def glcm_features(image, device=None):
     """Same call and return shape as the reference function (NB:269-308)."""
     image = np.asarray(image)
-    ex = get_extractor(device, basic=False, glcm=True)
-    batch, _, _ = _as_batch(image, None)
-    row = ex.extract_host_hwc(batch.astype(np.uint16, copy=False))[0]
-    return dict(zip(ex.columns(image.shape[2]), (float(v) for v in row)))
+    row = extract_features(image[None], basic=False, glcm=True, device=device)[0]    # same dtype / range checks
+    return dict(zip(schema.feature_columns(image.shape[2], basic=False, glcm=True), (float(v) for v in row)))

@@ -501,3 +501,22 @@ def test_k1_wide_range_falls_back_to_fp64(torch_mod):
     compare_tables(imf.extract_features(img), c_oracle.table(_planar(img)), cols, label="k1 range")
     compare_tables(imf.extract_features(img, mask), c_oracle.table(_planar(img), _planar(mask)), cols,
                    label="k1 range masked")
+
+
+def test_k1_fourth_power_sum_beyond_64_bits(torch_mod):
+    """Every |x - pivot| within the integer limit, but the tile's sum of fourth powers exceeds 2^64: large
+    mid-range tiles (128x128 uniform over ~20,000) and a bimodal 64x64 tile (0 / 18,000).  The lane sums
+    fit 64 bits, the warp total does not."""
+    rng = np.random.default_rng(32)
+    big = [rng.integers(0, 20001, (128, 128)), 30000 + rng.integers(0, 22001, (128, 128)),
+           np.where(rng.random((128, 128)) < 0.5, 0, 23000)]
+    img = np.stack([b.astype(np.uint16) for b in big], axis=2)[None]
+    cols = imf.feature_columns(img.shape[3])
+    compare_tables(imf.extract_features(img), c_oracle.table(_planar(img)), cols, label="k1 s4 128")
+    mask = (rng.random(img.shape) < 0.9).astype(np.uint8)
+    compare_tables(imf.extract_features(img, mask), c_oracle.table(_planar(img), _planar(mask)), cols,
+                   label="k1 s4 128 masked")
+    small = [np.where(rng.random((64, 64)) < 0.5, 0, 18000), np.where(rng.random((64, 64)) < 0.5, 100, 23100)]
+    img = np.stack([b.astype(np.uint16) for b in small], axis=2)[None]
+    cols = imf.feature_columns(img.shape[3])
+    compare_tables(imf.extract_features(img), c_oracle.table(_planar(img)), cols, label="k1 s4 bimodal")
