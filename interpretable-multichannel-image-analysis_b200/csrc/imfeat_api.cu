@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "k1_moments.cuh"
 #include "k2_order_entropy.cuh"
+#include "k12_basic.cuh"
 #include "k3_glcm.cuh"
 #include "k3_ring.cuh"
 #include "k4_shape.cuh"
@@ -29,7 +30,7 @@ constexpr int kWlSlots = 8;
 struct imfeat_ctx {
     int device;
     int sm_count;
-    int k1_bps[2], k4_bps[2], k2c_bps[2], k4w_bps[2];   // resident CTAs per SM (occupancy API), [masked]
+    int k1_bps[2], k4_bps[2], k2c_bps[2], k4w_bps[2], k12_bps[2];   // resident CTAs per SM (occupancy API), [masked]
     unsigned int* d_sched;      // ring of kSchedSlots x 8 work counters (one slot per extract call)
     unsigned int sched_head;
     uint32_t* d_worklist;       // [0] = count, [1..] = tile ids left to the full-range K2 kernel
@@ -55,7 +56,7 @@ struct imfeat_ctx {
     size_t in_bytes, out_bytes;
     // optional per-kernel timing (imfeat_enable_timing): a ring of event sets, resolved lazily
     // debugging / measurement switches, read from the environment once at imfeat_create
-    int env_k1_fp64, env_k1_tma, env_k2_compact, env_k4_warp, env_k2_groups, env_k3_threads, env_k3_chunk, env_k3_ring;
+    int env_k1_fp64, env_k1_tma, env_k2_compact, env_k4_warp, env_k2_groups, env_k3_threads, env_k3_chunk, env_k3_ring, env_k3_table, env_fuse12;
     int timing;
     int t_head, t_pending;
     cudaEvent_t t_ev[kTimingSlots][5];
@@ -154,6 +155,8 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
         ctx->env_k3_threads = flag("IMFEAT_K3_THREADS", 128) == 256 ? 256 : 128;   // threads per K3 CTA
         ctx->env_k3_chunk = flag("IMFEAT_K3_CHUNK", 16384);                        // objects per front/bins round of K3
         if (ctx->env_k3_chunk < 1) ctx->env_k3_chunk = 16384;
+        ctx->env_fuse12 = flag("IMFEAT_FUSE12", 1);          // 1: the basic block in one pass (k12_basic.cuh); 0: K1 then K2c
+        ctx->env_k3_table = flag("IMFEAT_K3_TABLE", 0);      // 32 / 64: force the table size of the bins kernel (0: by mask)
         ctx->env_k3_ring = flag("IMFEAT_K3_RING", 1);       // 1: unmasked tiles through the one-kernel ring variant (k3_ring.cuh)
     }
     ctx->sm_count = prop.multiProcessorCount;
@@ -181,14 +184,22 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
     free(tab);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_order_entropy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_order_entropy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false, 128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true, 128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false, 128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true, 128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false, 256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false, 256, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true, 256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true, 256, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false, 256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, false, 256, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true, 256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<true, true, 256, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ring::k3_glcm_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ring::k3_glcm_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k3a_front_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -200,6 +211,8 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k1_bps[1], k1_moments_kernel<true>, 256, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2c_bps[0], k2c_order_entropy_kernel<false>, kK2cThreads, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2c_bps[1], k2c_order_entropy_kernel<true>, kK2cThreads, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k12_bps[0], k12_basic_kernel<false>, 32, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k12_bps[1], k12_basic_kernel<true>, 32, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4w_bps[0], k4w_shape_kernel<false>, 32, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4w_bps[1], k4w_shape_kernel<true>, 32, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4_bps[0], k4_shape_kernel<false>, kK4Threads, sizeof(K4Smem));
@@ -274,13 +287,13 @@ static int grow_buffer(imfeat_ctx* ctx, cudaStream_t st, void** buf, size_t byte
 // output records), bins kernel (persistent CTAs of NT threads, as many as fit an SM: three for 64x64 tiles),
 // finalize kernel (raw sums -> the six properties).  Front and bins alternate over chunks of objects so that the
 // scratch records of a chunk are still in L2 when the bins kernel fetches them.
-template <bool DUMP, int NT>
+template <bool DUMP, int NT, int TB>
 static int launch_k3_nt(imfeat_ctx* ctx, bool masked, cudaStream_t st, const Params& P, int maxpx) {
     const size_t rec = k3_rec_bytes(maxpx, masked);
-    const size_t smem_b = k3_smem_bytes(maxpx, masked), smem_a = (size_t)kK3aWarps * k3a_warp_bytes(maxpx, masked);
+    const size_t smem_b = k3_smem_bytes(maxpx, masked, TB), smem_a = (size_t)kK3aWarps * k3a_warp_bytes(maxpx, masked);
     int bps_a = 0, bps_b = 0;
-    cudaError_t e = masked ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_b, k3_glcm_kernel<true, DUMP, NT>, NT, smem_b)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_b, k3_glcm_kernel<false, DUMP, NT>, NT, smem_b);
+    cudaError_t e = masked ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_b, k3_glcm_kernel<true, DUMP, NT, TB>, NT, smem_b)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_b, k3_glcm_kernel<false, DUMP, NT, TB>, NT, smem_b);
     if (e == cudaSuccess)
         e = masked ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_a, k3a_front_kernel<true>, 32 * kK3aWarps, smem_a)
                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_a, k3a_front_kernel<false>, 32 * kK3aWarps, smem_a);
@@ -311,8 +324,8 @@ static int launch_k3_nt(imfeat_ctx* ctx, bool masked, cudaStream_t st, const Par
         else k3a_front_kernel<false><<<grid_a, 32 * kK3aWarps, smem_a, st>>>(P, maxpx, (uint32_t)t0, nl, slot.ptr);
         const long long res_b = (long long)ctx->sm_count * bps_b;
         const int grid_b = (int)(nl < res_b ? nl : res_b);
-        if (masked) k3_glcm_kernel<true, DUMP, NT><<<grid_b, NT, smem_b, st>>>(P, maxpx, nl, slot.ptr);
-        else k3_glcm_kernel<false, DUMP, NT><<<grid_b, NT, smem_b, st>>>(P, maxpx, nl, slot.ptr);
+        if (masked) k3_glcm_kernel<true, DUMP, NT, TB><<<grid_b, NT, smem_b, st>>>(P, maxpx, nl, slot.ptr);
+        else k3_glcm_kernel<false, DUMP, NT, TB><<<grid_b, NT, smem_b, st>>>(P, maxpx, nl, slot.ptr);
         ctx->launches += 2;
     }
     const long long recs = P.n_tiles * P.n_angles;
@@ -328,8 +341,11 @@ static int launch_k3_nt(imfeat_ctx* ctx, bool masked, cudaStream_t st, const Par
 }
 template <bool DUMP>
 static int launch_k3(imfeat_ctx* ctx, bool masked, cudaStream_t st, const Params& P, int maxpx) {
-    return ctx->env_k3_threads == 128 ? launch_k3_nt<DUMP, 128>(ctx, masked, st, P, maxpx)
-                                      : launch_k3_nt<DUMP, 256>(ctx, masked, st, P, maxpx);
+    // masked tiles: 32 KB tables of 4-bit counters (their bins rarely hold more than a few pairs); unmasked: 64 KB of 8-bit
+    const bool small = ctx->env_k3_table ? ctx->env_k3_table == 32 : masked;
+    if (ctx->env_k3_threads == 128)
+        return small ? launch_k3_nt<DUMP, 128, 32>(ctx, masked, st, P, maxpx) : launch_k3_nt<DUMP, 128, 64>(ctx, masked, st, P, maxpx);
+    return small ? launch_k3_nt<DUMP, 256, 32>(ctx, masked, st, P, maxpx) : launch_k3_nt<DUMP, 256, 64>(ctx, masked, st, P, maxpx);
 }
 
 // K2: measured on B200 (10,000 64x64x12 objects): unmasked 1.59 ms with 4 groups vs 1.84 ms with 2;
@@ -441,32 +457,13 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
     const bool masked = P.masks != nullptr;
     const long long sm = ctx->sm_count;
     if (o->want_basic) {
-        const long long res1 = sm * (ctx->k1_bps[masked] > 0 ? ctx->k1_bps[masked] : 1);   // one resident wave
-        const int g1 = (int)((P.n_tiles + 7) / 8 < res1 ? (P.n_tiles + 7) / 8 : res1);
-        const bool use_tma = !masked && ctx->env_k1_tma == 1;   // measured: no faster than the direct path
-        if (use_tma) {
-            // shared-memory ring of whole tiles filled by cp.async.bulk; one persistent CTA per SM
-            const int stage_bytes = ((P.hs * P.ws * 2 + 127) & ~127);
-            int n_stages = (200 * 1024) / stage_bytes;
-            if (n_stages > 32) n_stages = 32;
-            const size_t smem = (size_t)n_stages * stage_bytes + 16 * (size_t)n_stages;
-            const int gt = (int)(P.n_tiles < sm ? P.n_tiles : sm);
-            k1_moments_tma_kernel<<<gt, kK1TmaThreads, smem, st>>>(P, n_stages, stage_bytes);
-        } else if (masked) k1_moments_kernel<true><<<g1, 256, 0, st>>>(P);
-        else k1_moments_kernel<false><<<g1, 256, 0, st>>>(P);
-        IMFEAT_MARK(0)
         const int g2 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
         const int ng2 = k2_groups(ctx);
-        if (ctx->env_k2_compact == 0) {
-            // full-range kernel for every tile
-            if (masked) k2_order_entropy_kernel<true><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, nullptr, nullptr);
-            else k2_order_entropy_kernel<false><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, nullptr, nullptr);
-            ctx->launches += 2;
-        } else {
-            // compact kernel first (value range < 4096, known from K1's min/max); it appends the
-            // remaining tiles to a worklist that the full-range ring kernel then works off
-            // the worklist lives in a ring of kWlSlots buffers: calls on different streams (e.g. the two
-            // streams of the host pipeline) may be in flight at the same time
+        const bool fuse12 = ctx->env_fuse12 != 0 && ctx->env_k2_compact != 0 && !(ctx->env_k1_tma == 1 && !masked);
+        // worklist of the tiles the compact histogram could not take (value range >= 4096): a ring of kWlSlots
+        // buffers, because calls on different streams (e.g. the two streams of the host pipeline) may be in flight
+        uint32_t* wl = nullptr;
+        if (ctx->env_k2_compact != 0) {
             if ((size_t)P.n_tiles + 1 > ctx->worklist_cap) {             // rare: the batch grew
                 size_t cap_new = (size_t)P.n_tiles + 1;
                 if (cap_new < 2 * ctx->worklist_cap) cap_new = 2 * ctx->worklist_cap;
@@ -475,17 +472,54 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
                 if (rcw) return rcw;
                 ctx->worklist_cap = cap_new;
             }
-            uint32_t* wl = ctx->d_worklist + (size_t)(ctx->wl_head++ % kWlSlots) * ctx->worklist_cap;
+            wl = ctx->d_worklist + (size_t)(ctx->wl_head++ % kWlSlots) * ctx->worklist_cap;
             CU(cudaMemsetAsync(wl, 0, sizeof(uint32_t), st));
-            const long long resc = sm * (ctx->k2c_bps[masked] > 0 ? ctx->k2c_bps[masked] : 1);
-            const int gc = (int)(P.n_tiles < resc ? P.n_tiles : resc);
-            if (masked) k2c_order_entropy_kernel<true><<<gc, kK2cThreads, 0, st>>>(P, wl + 1, wl);
-            else k2c_order_entropy_kernel<false><<<gc, kK2cThreads, 0, st>>>(P, wl + 1, wl);
+        }
+        if (fuse12) {
+            // the whole basic block in one pass over the pixels; tiles whose histogram window did not hold are
+            // left to the full-range kernel
+            const long long res = sm * (ctx->k12_bps[masked] > 0 ? ctx->k12_bps[masked] : 1);
+            const int g = (int)(P.n_tiles < res ? P.n_tiles : res);
+            if (masked) k12_basic_kernel<true><<<g, 32, 0, st>>>(P, wl + 1, wl);
+            else k12_basic_kernel<false><<<g, 32, 0, st>>>(P, wl + 1, wl);
+            IMFEAT_MARK(0)
             if (masked) k2_order_entropy_kernel<true><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, wl + 1, wl);
             else k2_order_entropy_kernel<false><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, wl + 1, wl);
-            ctx->launches += 3;
+            ctx->launches += 2;
+            IMFEAT_MARK(1)
+        } else {
+            const long long res1 = sm * (ctx->k1_bps[masked] > 0 ? ctx->k1_bps[masked] : 1);   // one resident wave
+            const int g1 = (int)((P.n_tiles + 7) / 8 < res1 ? (P.n_tiles + 7) / 8 : res1);
+            const bool use_tma = !masked && ctx->env_k1_tma == 1;   // measured: no faster than the direct path
+            if (use_tma) {
+                // shared-memory ring of whole tiles filled by cp.async.bulk; one persistent CTA per SM
+                const int stage_bytes = ((P.hs * P.ws * 2 + 127) & ~127);
+                int n_stages = (200 * 1024) / stage_bytes;
+                if (n_stages > 32) n_stages = 32;
+                const size_t smem = (size_t)n_stages * stage_bytes + 16 * (size_t)n_stages;
+                const int gt = (int)(P.n_tiles < sm ? P.n_tiles : sm);
+                k1_moments_tma_kernel<<<gt, kK1TmaThreads, smem, st>>>(P, n_stages, stage_bytes);
+            } else if (masked) k1_moments_kernel<true><<<g1, 256, 0, st>>>(P);
+            else k1_moments_kernel<false><<<g1, 256, 0, st>>>(P);
+            IMFEAT_MARK(0)
+            if (ctx->env_k2_compact == 0) {
+                // full-range kernel for every tile
+                if (masked) k2_order_entropy_kernel<true><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, nullptr, nullptr);
+                else k2_order_entropy_kernel<false><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, nullptr, nullptr);
+                ctx->launches += 2;
+            } else {
+                // compact kernel first (value range < 4096, known from K1's min/max); it appends the
+                // remaining tiles to the worklist that the full-range ring kernel then works off
+                const long long resc = sm * (ctx->k2c_bps[masked] > 0 ? ctx->k2c_bps[masked] : 1);
+                const int gc = (int)(P.n_tiles < resc ? P.n_tiles : resc);
+                if (masked) k2c_order_entropy_kernel<true><<<gc, kK2cThreads, 0, st>>>(P, wl + 1, wl);
+                else k2c_order_entropy_kernel<false><<<gc, kK2cThreads, 0, st>>>(P, wl + 1, wl);
+                if (masked) k2_order_entropy_kernel<true><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, wl + 1, wl);
+                else k2_order_entropy_kernel<false><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, wl + 1, wl);
+                ctx->launches += 3;
+            }
+            IMFEAT_MARK(1)
         }
-        IMFEAT_MARK(1)
     }
     // K4 goes before K3: with several GPUs the all-gather of the previous batch then overlaps the
     // dynamically scheduled warp-per-tile kernels (K1, K2c, K4w) and is over when K3 starts, whose

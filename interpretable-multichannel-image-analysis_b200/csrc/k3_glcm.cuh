@@ -64,20 +64,19 @@ __host__ __device__ inline size_t k3_rec_bytes(int max_pixels, bool masked) {
     return sizeof(K3Hdr) + 4 * (size_t)(k3_q8_words(max_pixels) + k3_mb_words(max_pixels, masked));
 }
 
-struct alignas(16) K3Smem {
-    uint32_t hist[16384];                       // 65,536 bins x 8 bit (fallback: 32,768 bins x 16 bit)
+struct alignas(16) K3Smem {                     // behind the table (64 or 32 KB), before the two record buffers
     uint32_t part[2][kK3MaxWarps][2];           // per direction parity and warp: sum of squares, counts taken back
     unsigned long long mbar[2];                 // completion of the bulk copy into record buffer 0 / 1
     uint32_t tq[4];                             // local tile indices drawn from the global counter
-    uint32_t slow[2];                           // fallback sum of squares; dense count check of the dump
-    uint32_t pad[2];
+    uint32_t slow[4];                           // fallback: sum of squares, [1] dense count check of the dump, [2] counts taken back
 };
 struct K3Group {                               // where the quantised tile and its mask bits live
     uint32_t* q8;                              // quantised pixels (bytes) + slack for unaligned reads
     uint32_t* mbits;                           // one bit per pixel: inside the mask (masked variant)
 };
-__host__ __device__ inline size_t k3_smem_bytes(int max_pixels, bool masked) {
-    return sizeof(K3Smem) + 2 * k3_rec_bytes(max_pixels, masked);      // two record buffers: the next tile lands while this one is worked off
+__host__ __device__ inline size_t k3_smem_bytes(int max_pixels, bool masked, int table_kb) {
+    // two record buffers: the next tile lands while this one is worked off
+    return (size_t)table_kb * 1024 + sizeof(K3Smem) + 2 * k3_rec_bytes(max_pixels, masked);
 }
 // front kernel: per warp one record being assembled + the four output records
 constexpr int kK3aWarps = 4;                    // warps per CTA of the front kernel
@@ -221,16 +220,25 @@ __device__ __forceinline__ void k3_sums(const double* homtab, uint32_t I4, uint3
 }
 
 // ---- the bins ------------------------------------------------------------------------------------
-// Bin (i, j) is an 8-bit counter: byte j >> 6 of word (i << 6) | ((j & 63) ^ ((i & 15) << 2)).  The four
-// bins of a word are 64 gray levels apart, so the similar levels of neighbouring pixels land in different
-// words, and the word index is swizzled with i because the bank would otherwise depend on j alone
-// (simulated on the synthetic tiles: 3.9 wavefronts per warp-wide atomic, against 6.3 for the plain
+// The counters of one (tile, direction) live in a table of TB = 64 KB (unmasked tiles) or 32 KB (masked
+// tiles, whose bins rarely hold more than a handful of pairs: five CTAs fit an SM instead of three).  The
+// table is used in one of these modes; the pairs that do not take part in a pass add 0:
+//   MODE 0      64 KB  8-bit counters, all pairs      bin (i, j): byte j >> 6 of word i << 6 | x, x = (j & 63) ^ (i & 15) << 2
+//   MODE 1, 2   64 KB  16-bit counters, i even / odd  bin (i >> 1, j): half j & 1 of word (i >> 1) << 7 | j >> 1
+//   MODE 3      32 KB  4-bit counters, all pairs      bin (i, j): nibble j >> 5 of word i << 5 | x, x = (j & 31) ^ (i & 7) << 2
+//   MODE 4, 5   32 KB  8-bit counters, i even / odd   bin (i >> 1, j): byte j >> 6 of word (i >> 1) << 6 | x, x = (j & 63) ^ (i >> 1 & 15) << 2
+//   MODE 6..9   32 KB  16-bit counters, i & 3 = 0..3  bin (i >> 2, j): half j & 1 of word (i >> 2) << 7 | j >> 1
+// In the packed modes the bins of a word are 64 (32) gray levels apart, so the similar levels of neighbouring
+// pixels land in different words, and the word index is swizzled with i because the bank would otherwise depend
+// on j alone (simulated on the synthetic tiles: 3.9 wavefronts per warp-wide atomic, against 6.3 for the plain
 // layout and 3.5 for uniformly random words; measured: 3.96).
-// MODE 0: the 8-bit table above.  For four pairs at once: X = byte offset of the word inside row i,
-// R = the row byte (i), H = the shift of the increment (8 * (j >> 6)), E = 1 per pair that takes part.
-// MODE 1 / 2 (fallback): 16-bit counters for the pairs with even / odd i only: bin (i >> 1, j) is half
-// j & 1 of word (i >> 1) << 7 | j >> 1 (byte offset i7..i1 j7..j1 00: the top bit of j goes into the
-// row byte); the other pairs add 0.
+// k3_pack4 works on four pairs at once: R / X = high / low byte of the word's byte offset (shifted left by one
+// in the 32 KB modes so that both fit a byte), H = shift of the increment, E = 1 per pair that takes part.
+template <int MODE> struct K3Mode {
+    static constexpr int kTableKB = MODE <= 2 ? 64 : 32;
+    static constexpr int kAddrShift = MODE <= 2 ? 16 : 17;
+    static constexpr int kBits = (MODE == 0 || MODE == 4 || MODE == 5) ? 8 : (MODE == 3 ? 4 : 16);
+};
 template <int MODE>
 __device__ __forceinline__ void k3_pack4(uint32_t I4, uint32_t J4, uint32_t V1, uint32_t& X, uint32_t& R, uint32_t& H, uint32_t& E) {
     if (MODE == 0) {
@@ -238,18 +246,35 @@ __device__ __forceinline__ void k3_pack4(uint32_t I4, uint32_t J4, uint32_t V1, 
         R = I4;
         H = (J4 >> 3) & 0x18181818u;
         E = V1;
-    } else {
+    } else if (MODE <= 2) {                        // byte offset i7..i1 j7..j1 00: the top bit of j goes into the row byte
         X = (J4 << 1) & 0xfcfcfcfcu;
         R = (I4 & 0xfefefefeu) | ((J4 >> 7) & 0x01010101u);
         H = (J4 << 4) & 0x10101010u;
         E = V1 & (MODE == 1 ? ~I4 : I4);           // V1 has only bit 0 of each byte
+    } else if (MODE == 3) {                        // twice the byte offset: i7..i0 x4..x0 000
+        X = ((J4 << 3) & 0xf8f8f8f8u) ^ ((I4 << 5) & 0xe0e0e0e0u);
+        R = I4;
+        H = (J4 >> 3) & 0x1c1c1c1cu;               // 4 * (j >> 5)
+        E = V1;
+    } else if (MODE <= 5) {                        // twice the byte offset: i7..i1 x5..x0 000
+        const uint32_t XS = (J4 & 0x3f3f3f3fu) ^ ((I4 << 1) & 0x3c3c3c3cu);
+        X = (XS << 3) & 0xf8f8f8f8u;
+        R = (I4 & 0xfefefefeu) | ((XS >> 5) & 0x01010101u);
+        H = (J4 >> 3) & 0x18181818u;
+        E = V1 & (MODE == 4 ? ~I4 : I4);
+    } else {                                       // twice the byte offset: i7..i2 j7..j1 000
+        X = (J4 << 2) & 0xf8f8f8f8u;
+        R = (I4 & 0xfcfcfcfcu) | ((J4 >> 6) & 0x03030303u);
+        H = (J4 << 4) & 0x10101010u;
+        const uint32_t t = I4 ^ ((uint32_t)(MODE - 6) * 0x01010101u);
+        E = V1 & ~(t | (t >> 1));                  // the two low bits of i match
     }
 }
 // shared-window address of the word of pair K (0..3) of a group
-template <int K>
+template <int K, int SHIFT>
 __device__ __forceinline__ uint32_t k3_addr(uint32_t hist_addr, uint32_t X, uint32_t R) {
     constexpr uint32_t sel = ((4u + K) << 12) | ((uint32_t)K << 8) | ((4u + K) << 4) | (uint32_t)K;
-    return hist_addr + (__byte_perm(X, R, sel) >> 16);           // row << 8 | x
+    return hist_addr + (__byte_perm(X, R, sel) >> SHIFT);        // R << 8 | X, halved in the 32 KB modes
 }
 // increment of pair K: 1 << shift if the pair takes part (E: byte K = 1), else 0 -- the add then
 // changes nothing, on whatever word the bytes lying there give, and the build phase is branch-free
@@ -266,9 +291,13 @@ template <int MODE>
 __device__ __forceinline__ void k3_take(uint32_t addr, uint32_t& sq, uint32_t& cnt) {
     uint32_t old;
     asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(0u) : "memory");
-    if (MODE == 0) {
+    if (K3Mode<MODE>::kBits == 8) {
         sq = __dp4a(old, old, sq);
         cnt = __dp4a(old, 0x01010101u, cnt);
+    } else if (K3Mode<MODE>::kBits == 4) {
+        const uint32_t lo = old & 0x0f0f0f0fu, hi = (old >> 4) & 0x0f0f0f0fu;
+        sq = __dp4a(hi, hi, __dp4a(lo, lo, sq));
+        cnt = __dp4a(lo + hi, 0x01010101u, cnt);
     } else {
         const uint32_t c0 = old & 0xffffu, c1 = old >> 16;
         sq += c0 * c0 + c1 * c1;
@@ -277,20 +306,60 @@ __device__ __forceinline__ void k3_take(uint32_t addr, uint32_t& sq, uint32_t& c
 }
 template <int MODE>
 __device__ __forceinline__ void k3_build4(uint32_t hist_addr, uint32_t I4, uint32_t J4, uint32_t V1, uint32_t (&keep)[4]) {
+    constexpr int SH = K3Mode<MODE>::kAddrShift;
     uint32_t X, R, H, E;
     k3_pack4<MODE>(I4, J4, V1, X, R, H, E);
-    keep[0] = k3_addr<0>(hist_addr, X, R); keep[1] = k3_addr<1>(hist_addr, X, R);
-    keep[2] = k3_addr<2>(hist_addr, X, R); keep[3] = k3_addr<3>(hist_addr, X, R);
+    keep[0] = k3_addr<0, SH>(hist_addr, X, R); keep[1] = k3_addr<1, SH>(hist_addr, X, R);
+    keep[2] = k3_addr<2, SH>(hist_addr, X, R); keep[3] = k3_addr<3, SH>(hist_addr, X, R);
     k3_red(keep[0], k3_inc<0>(H, E));
     k3_red(keep[1], k3_inc<1>(H, E));
     k3_red(keep[2], k3_inc<2>(H, E));
     k3_red(keep[3], k3_inc<3>(H, E));
 }
+template <int MODE>
+__device__ __forceinline__ void k3_take4(uint32_t hist_addr, uint32_t I4, uint32_t J4, uint32_t& sq, uint32_t& cnt) {
+    constexpr int SH = K3Mode<MODE>::kAddrShift;
+    uint32_t X, R, H, E;
+    k3_pack4<MODE>(I4, J4, 0u, X, R, H, E);
+    k3_take<MODE>(k3_addr<0, SH>(hist_addr, X, R), sq, cnt);
+    k3_take<MODE>(k3_addr<1, SH>(hist_addr, X, R), sq, cnt);
+    k3_take<MODE>(k3_addr<2, SH>(hist_addr, X, R), sq, cnt);
+    k3_take<MODE>(k3_addr<3, SH>(hist_addr, X, R), sq, cnt);
+}
+// parity dump: the bins the table holds in this mode, as 32-bit counts at dump[i * 256 + j]
+template <int MODE, int NT>
+__device__ __forceinline__ void k3_dump_table(const uint32_t* hist, uint32_t* dump) {
+    constexpr int words = K3Mode<MODE>::kTableKB * 256;
+    for (int k = threadIdx.x; k < words; k += NT) {
+        const uint32_t wv = hist[k], uk = (uint32_t)k;
+        if (MODE == 0) {
+            const uint32_t i = uk >> 6, jl = (uk & 63u) ^ ((i & 15u) << 2);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dump[i * 256u + jl + 64u * q] = (wv >> (8 * q)) & 0xffu;
+        } else if (MODE <= 2) {
+            const uint32_t i = 2u * (uk >> 7) + (MODE == 2 ? 1u : 0u), j0 = (uk & 127u) * 2u;
+            reinterpret_cast<uint2*>(dump)[(i * 256u + j0) >> 1] = make_uint2(wv & 0xffffu, wv >> 16);
+        } else if (MODE == 3) {
+            const uint32_t i = uk >> 5, jl = (uk & 31u) ^ ((i & 7u) << 2);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dump[i * 256u + jl + 32u * q] = (wv >> (4 * q)) & 0xfu;
+        } else if (MODE <= 5) {
+            const uint32_t ih = uk >> 6, jl = (uk & 63u) ^ ((ih & 15u) << 2), i = 2u * ih + (MODE == 5 ? 1u : 0u);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dump[i * 256u + jl + 64u * q] = (wv >> (8 * q)) & 0xffu;
+        } else {
+            const uint32_t i = 4u * (uk >> 7) + (uint32_t)(MODE - 6), j0 = (uk & 127u) * 2u;
+            reinterpret_cast<uint2*>(dump)[(i * 256u + j0) >> 1] = make_uint2(wv & 0xffffu, wv >> 16);
+        }
+    }
+}
 
-// ---- fallback: 16-bit counters, two passes over half the key space each (even i, odd i) -----------------
-// Only reached when an 8-bit counter wrapped.  Leaves the sum of squared counts in S.slow[0].
+// ---- fallback passes: wider counters over a slice of the key space each --------------------------------------
+// Only reached when a counter of the first attempt wrapped.  Adds the squared counts to S.slow[0] and the
+// counts taken back to S.slow[2] (equal to the number of pairs unless a counter of these passes wrapped too).
 template <bool MASKED, bool DUMP, int NT, int NG, int MODE>
-__device__ __forceinline__ uint32_t k3_slow_pass(K3Smem& S, const K3Group& Gp, const K3Geom& G, uint32_t hist_addr, uint32_t* dump) {
+__device__ __forceinline__ void k3_slow_pass(K3Smem& S, const uint32_t* hist, const K3Group& Gp, const K3Geom& G,
+                                             uint32_t hist_addr, uint32_t* dump, uint32_t& sq, uint32_t& cnt) {
     const int tid = threadIdx.x;
     for (int item = tid; item < G.items; item += NT) {
         uint32_t I4[NG], J4[NG], pm, unused[4];
@@ -301,36 +370,33 @@ __device__ __forceinline__ uint32_t k3_slow_pass(K3Smem& S, const K3Group& Gp, c
     }
     __syncthreads();
     if (DUMP) {
-        for (int k = tid; k < 16384; k += NT) {
-            const uint32_t wv = S.hist[k];
-            const uint32_t i = 2u * ((uint32_t)k >> 7) + (MODE == 2 ? 1u : 0u), j0 = ((uint32_t)k & 127u) * 2u;
-            reinterpret_cast<uint2*>(dump)[(i * 256u + j0) >> 1] = make_uint2(wv & 0xffffu, wv >> 16);
-        }
+        k3_dump_table<MODE, NT>(hist, dump);
         __syncthreads();
     }
-    uint32_t sq = 0u, cnt = 0u;
     for (int item = tid; item < G.items; item += NT) {
         uint32_t I4[NG], J4[NG], pm;
         if (!k3_item<MASKED, NG>(Gp, G, item, I4, J4, pm)) continue;
 #pragma unroll
-        for (int k = 0; k < NG; ++k) {
-            uint32_t X, R, H, E;
-            k3_pack4<MODE>(I4[k], J4[k], 0u, X, R, H, E);
-            k3_take<MODE>(k3_addr<0>(hist_addr, X, R), sq, cnt);
-            k3_take<MODE>(k3_addr<1>(hist_addr, X, R), sq, cnt);
-            k3_take<MODE>(k3_addr<2>(hist_addr, X, R), sq, cnt);
-            k3_take<MODE>(k3_addr<3>(hist_addr, X, R), sq, cnt);
-        }
+        for (int k = 0; k < NG; ++k) k3_take4<MODE>(hist_addr, I4[k], J4[k], sq, cnt);
     }
     __syncthreads();
-    return sq;
 }
-template <bool MASKED, bool DUMP, int NT, int NG>
-__device__ __noinline__ void k3_slow_direction(K3Smem& S, const K3Group& Gp, const K3Geom& G, uint32_t hist_addr, uint32_t* dump) {
-    uint32_t sq = k3_slow_pass<MASKED, DUMP, NT, NG, 1>(S, Gp, G, hist_addr, dump);
-    sq += k3_slow_pass<MASKED, DUMP, NT, NG, 2>(S, Gp, G, hist_addr, dump);
+template <bool MASKED, bool DUMP, int NT, int NG, int FIRST, int NPASS>
+__device__ __noinline__ void k3_slow_direction(K3Smem& S, const uint32_t* hist, const K3Group& Gp, const K3Geom& G,
+                                               uint32_t hist_addr, uint32_t* dump) {
+    uint32_t sq = 0u, cnt = 0u;
+    k3_slow_pass<MASKED, DUMP, NT, NG, FIRST>(S, hist, Gp, G, hist_addr, dump, sq, cnt);
+    k3_slow_pass<MASKED, DUMP, NT, NG, FIRST + 1>(S, hist, Gp, G, hist_addr, dump, sq, cnt);
+    if (NPASS == 4) {
+        k3_slow_pass<MASKED, DUMP, NT, NG, FIRST + 2>(S, hist, Gp, G, hist_addr, dump, sq, cnt);
+        k3_slow_pass<MASKED, DUMP, NT, NG, FIRST + 3>(S, hist, Gp, G, hist_addr, dump, sq, cnt);
+    }
     sq = __reduce_add_sync(0xffffffffu, sq);
-    if ((threadIdx.x & 31) == 0 && sq) atomicAdd(&S.slow[0], sq);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) {
+        if (sq) atomicAdd(&S.slow[0], sq);
+        if (cnt) atomicAdd(&S.slow[2], cnt);
+    }
     __syncthreads();
 }
 
@@ -538,11 +604,16 @@ k3a_front_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t tile
 }
 
 // ---- K3b, the bins kernel ------------------------------------------------------------------------------------
-template <bool MASKED, bool DUMP, int NT>
-__global__ void __launch_bounds__(NT, 3)
+// TB = 64: 8-bit counters first (MODE 0), 16-bit halves if one wrapped.  TB = 32: 4-bit counters first
+// (MODE 3), 8-bit halves if one wrapped, 16-bit quarters if one of those wrapped too; a CTA that has just seen
+// a wrap starts the next directions with the 8-bit halves at once.
+template <bool MASKED, bool DUMP, int NT, int TB>
+__global__ void __launch_bounds__(NT, TB == 64 ? 3 : 5)
 k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t n_local, const unsigned char* __restrict__ scratch) {
     extern __shared__ __align__(16) unsigned char k3_smem_raw[];
-    K3Smem& S = *reinterpret_cast<K3Smem*>(k3_smem_raw);
+    uint32_t* const hist = reinterpret_cast<uint32_t*>(k3_smem_raw);
+    K3Smem& S = *reinterpret_cast<K3Smem*>(k3_smem_raw + TB * 1024);
+    constexpr int M0 = TB == 64 ? 0 : 3;         // the mode of the first attempt
     constexpr int NG = MASKED ? 2 : 4;           // groups of 4 pairs per item
     constexpr int NP = 4 * NG;
     constexpr int KC = 4096 / (NT * NP);         // items per thread whose word addresses stay in registers (a 64x64 tile in full)
@@ -550,16 +621,16 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t n_loca
     static_assert(NW <= kK3MaxWarps && KC >= 1, "CTA size");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rec_bytes = (uint32_t)k3_rec_bytes(max_pixels, MASKED);
-    unsigned char* recbuf0 = k3_smem_raw + sizeof(K3Smem);
-    const uint32_t hist_addr = smem_addr(S.hist), bar0 = smem_addr(&S.mbar[0]), rec_addr0 = smem_addr(recbuf0);
+    unsigned char* recbuf0 = k3_smem_raw + TB * 1024 + sizeof(K3Smem);
+    const uint32_t hist_addr = smem_addr(hist), bar0 = smem_addr(&S.mbar[0]), rec_addr0 = smem_addr(recbuf0);
 
-    for (int k = tid; k < 16384; k += NT) S.hist[k] = 0u;
+    for (int k = tid; k < TB * 256; k += NT) hist[k] = 0u;
     if (tid == 0) {
         // tiles: the first one is the CTA's own index, the others come from the per-launch counter (so the
         // tail does not depend on how many CTAs are resident at once), drawn two tiles ahead
         S.tq[0] = blockIdx.x;
         S.tq[1] = gridDim.x + atomicAdd(P.sched + 6, 1u);
-        S.slow[0] = 0u; S.slow[1] = 0u;
+        S.slow[0] = 0u; S.slow[1] = 0u; S.slow[2] = 0u;
         mbar_init(bar0, 1);
         mbar_init(bar0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -574,6 +645,7 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t n_loca
     };
     if (tid == 0 && blockIdx.x < n_local) fetch(blockIdx.x, 0u);
     uint32_t dcount = 0u;                        // directions done by this CTA: its parity picks the partial-sum bank
+    int prefer_wide = 0;                         // TB = 32: directions left that skip the 4-bit attempt
 
     for (uint32_t j = 0;; ++j) {
         const uint32_t tl = S.tq[j & 3u];
@@ -595,90 +667,99 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t n_loca
         for (int a = 0; a < P.n_angles; ++a, ++dcount) {
             const K3Geom G = H.geom[a];
             const int par = (int)(dcount & 1u);
-            uint32_t adr[KC][NP];
-            uint32_t valid = 0u;
-            // ---- build: every existing pair adds 1 to its bin ----
-#pragma unroll
-            for (int i = 0; i < KC; ++i) {
-                const int item = tid + i * NT;
-                uint32_t I4[NG], J4[NG], pm;
-                if (item < G.items && k3_item<MASKED, NG>(Gp, G, item, I4, J4, pm)) {
-#pragma unroll
-                    for (int k = 0; k < NG; ++k) {
-                        uint32_t k4[4];
-                        k3_build4<0>(hist_addr, I4[k], J4[k], (((pm >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u, k4);
-                        adr[i][4 * k] = k4[0]; adr[i][4 * k + 1] = k4[1]; adr[i][4 * k + 2] = k4[2]; adr[i][4 * k + 3] = k4[3];
-                    }
-                    valid |= 1u << i;
-                }
-            }
-            for (int item = tid + KC * NT; item < G.items; item += NT) {
-                uint32_t I4[NG], J4[NG], pm, unused[4];
-                if (k3_item<MASKED, NG>(Gp, G, item, I4, J4, pm)) {
-#pragma unroll
-                    for (int k = 0; k < NG; ++k)
-                        k3_build4<0>(hist_addr, I4[k], J4[k], (((pm >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u, unused);
-                }
-            }
             const uint32_t M = (uint32_t)G.pad[0];         // pairs of this direction (front kernel)
-            __syncthreads();                               // ---- bins of this direction complete ----
             uint32_t* dump = nullptr;
-            if (DUMP) {
-                // parity dump of the raw bins: the 8-bit table if no counter wrapped (checked densely here),
-                // else from the 16-bit passes of the fallback below
-                dump = P.counts + ((long long)H.tile * P.n_angles + a) * 65536ll;
-                uint32_t dsum = 0u;
-                for (int k = tid; k < 16384; k += NT) dsum = __dp4a(S.hist[k], 0x01010101u, dsum);
-                dsum = __reduce_add_sync(0xffffffffu, dsum);
-                if (lane == 0 && dsum) atomicAdd(&S.slow[1], dsum);
-                __syncthreads();
-                const bool ok = S.slow[1] == M;
-                if (ok)
-                    for (int k = tid; k < 16384; k += NT) {
-                        const uint32_t wv = S.hist[k], i = (uint32_t)k >> 6;
-                        const uint32_t jl = ((uint32_t)k & 63u) ^ ((i & 15u) << 2);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) dump[i * 256u + jl + 64u * q] = (wv >> (8 * q)) & 0xffu;
-                    }
-                __syncthreads();
-                if (tid == 0) S.slow[1] = 0u;
-            }
-            // ---- clear: take the counts back, summing their squares ----
-            uint32_t sq = 0u, cnt = 0u;
-#pragma unroll
-            for (int i = 0; i < KC; ++i)
-                if (valid & (1u << i)) {
-#pragma unroll
-                    for (int k = 0; k < NP; ++k) k3_take<0>(adr[i][k], sq, cnt);
-                }
-            for (int item = tid + KC * NT; item < G.items; item += NT) {
-                uint32_t I4[NG], J4[NG], pm;
-                if (k3_item<MASKED, NG>(Gp, G, item, I4, J4, pm)) {
-#pragma unroll
-                    for (int k = 0; k < NG; ++k) {
-                        uint32_t X, R, Hs, E;
-                        k3_pack4<0>(I4[k], J4[k], 0u, X, R, Hs, E);
-                        k3_take<0>(k3_addr<0>(hist_addr, X, R), sq, cnt);
-                        k3_take<0>(k3_addr<1>(hist_addr, X, R), sq, cnt);
-                        k3_take<0>(k3_addr<2>(hist_addr, X, R), sq, cnt);
-                        k3_take<0>(k3_addr<3>(hist_addr, X, R), sq, cnt);
-                    }
-                }
-            }
-            sq = __reduce_add_sync(0xffffffffu, sq);
-            cnt = __reduce_add_sync(0xffffffffu, cnt);
-            if (lane == 0) { S.part[par][warp][0] = sq; S.part[par][warp][1] = cnt; }
-            if (tid == 0 && a + 1 == P.n_angles) S.tq[(j + 2) & 3u] = t_draw;
-            __syncthreads();                               // ---- table clean, sums complete ----
+            if (DUMP) dump = P.counts + ((long long)H.tile * P.n_angles + a) * 65536ll;
             uint32_t sqt = 0u, cntt = 0u;
+            const bool first = !(TB == 32 && prefer_wide > 0);
+            if (first) {
+                uint32_t adr[KC][NP];
+                uint32_t valid = 0u;
+                // ---- build: every existing pair adds 1 to its bin ----
 #pragma unroll
-            for (int w = 0; w < NW; ++w) { sqt += S.part[par][w][0]; cntt += S.part[par][w][1]; }
+                for (int i = 0; i < KC; ++i) {
+                    const int item = tid + i * NT;
+                    uint32_t I4[NG], J4[NG], pm;
+                    if (item < G.items && k3_item<MASKED, NG>(Gp, G, item, I4, J4, pm)) {
+#pragma unroll
+                        for (int k = 0; k < NG; ++k) {
+                            uint32_t k4[4];
+                            k3_build4<M0>(hist_addr, I4[k], J4[k], (((pm >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u, k4);
+                            adr[i][4 * k] = k4[0]; adr[i][4 * k + 1] = k4[1]; adr[i][4 * k + 2] = k4[2]; adr[i][4 * k + 3] = k4[3];
+                        }
+                        valid |= 1u << i;
+                    }
+                }
+                for (int item = tid + KC * NT; item < G.items; item += NT) {
+                    uint32_t I4[NG], J4[NG], pm, unused[4];
+                    if (k3_item<MASKED, NG>(Gp, G, item, I4, J4, pm)) {
+#pragma unroll
+                        for (int k = 0; k < NG; ++k)
+                            k3_build4<M0>(hist_addr, I4[k], J4[k], (((pm >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u, unused);
+                    }
+                }
+                __syncthreads();                           // ---- bins of this direction complete ----
+                if (DUMP) {
+                    // parity dump of the raw bins: this table if no counter wrapped (checked densely here),
+                    // else from the passes of the fallback below
+                    uint32_t dsum = 0u;
+                    for (int k = tid; k < TB * 256; k += NT) {
+                        const uint32_t wv = hist[k];
+                        dsum = TB == 64 ? __dp4a(wv, 0x01010101u, dsum)
+                                        : __dp4a((wv & 0x0f0f0f0fu) + ((wv >> 4) & 0x0f0f0f0fu), 0x01010101u, dsum);
+                    }
+                    dsum = __reduce_add_sync(0xffffffffu, dsum);
+                    if (lane == 0 && dsum) atomicAdd(&S.slow[1], dsum);
+                    __syncthreads();
+                    if (S.slow[1] == M) k3_dump_table<M0, NT>(hist, dump);
+                    __syncthreads();
+                    if (tid == 0) S.slow[1] = 0u;
+                }
+                // ---- clear: take the counts back, summing their squares ----
+                uint32_t sq = 0u, cnt = 0u;
+#pragma unroll
+                for (int i = 0; i < KC; ++i)
+                    if (valid & (1u << i)) {
+#pragma unroll
+                        for (int k = 0; k < NP; ++k) k3_take<M0>(adr[i][k], sq, cnt);
+                    }
+                for (int item = tid + KC * NT; item < G.items; item += NT) {
+                    uint32_t I4[NG], J4[NG], pm;
+                    if (k3_item<MASKED, NG>(Gp, G, item, I4, J4, pm)) {
+#pragma unroll
+                        for (int k = 0; k < NG; ++k) k3_take4<M0>(hist_addr, I4[k], J4[k], sq, cnt);
+                    }
+                }
+                sq = __reduce_add_sync(0xffffffffu, sq);
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                if (lane == 0) { S.part[par][warp][0] = sq; S.part[par][warp][1] = cnt; }
+                if (tid == 0 && a + 1 == P.n_angles) S.tq[(j + 2) & 3u] = t_draw;
+                __syncthreads();                           // ---- table clean, sums complete ----
+#pragma unroll
+                for (int w = 0; w < NW; ++w) { sqt += S.part[par][w][0]; cntt += S.part[par][w][1]; }
+            } else {
+                --prefer_wide;
+                if (tid == 0 && a + 1 == P.n_angles) S.tq[(j + 2) & 3u] = t_draw;
+                cntt = M + 1u;                             // straight to the wider counters
+            }
             if (cntt != M) {
-                // an 8-bit counter wrapped (a carry changes the sum of the counts): exact 16-bit passes
-                k3_slow_direction<MASKED, DUMP, NT, NG>(S, Gp, G, hist_addr, dump);
+                // a counter wrapped (a carry changes the sum of the counts): exact passes with wider counters
+                if (TB == 64) {
+                    k3_slow_direction<MASKED, DUMP, NT, NG, 1, 2>(S, hist, Gp, G, hist_addr, dump);
+                } else {
+                    if (first) prefer_wide = 16;
+                    if (!DUMP) k3_slow_direction<MASKED, false, NT, NG, 4, 2>(S, hist, Gp, G, hist_addr, dump);
+                    const bool again = DUMP || S.slow[2] != M;
+                    __syncthreads();
+                    if (again) {
+                        if (tid == 0) { S.slow[0] = 0u; S.slow[2] = 0u; }
+                        __syncthreads();
+                        k3_slow_direction<MASKED, DUMP, NT, NG, 6, 4>(S, hist, Gp, G, hist_addr, dump);
+                    }
+                }
                 sqt = S.slow[0];
                 __syncthreads();
-                if (tid == 0) S.slow[0] = 0u;
+                if (tid == 0) { S.slow[0] = 0u; S.slow[2] = 0u; }
             }
             if (tid == 0) H.rec[a * kK3Rec + kR_sq] = sqt;
         }
