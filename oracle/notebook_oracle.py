@@ -26,7 +26,7 @@ Pinning status
 --------------
 * basic features: PINNED.  ``tests/golden/make_golden.py`` executes the notebook's own
   cell 13 (loaded from /root/reference at generation time) on seeded inputs and the
-  committed fixtures are compared with this module in ``tests/test_oracle_golden.py``.
+  committed fixtures are compared with this module in ``tests/test_oracle_cpu.py``.
 * GLCM features: pinned against scikit-image's published docstring example for
   ``greycomatrix`` and its ``test_texture.py`` property values, and
   against cell 13 executed with the restated skimage functions injected.  The real
@@ -319,14 +319,11 @@ def shape_values(mask):
     if area == 0:
         return [0.0, 0.0] + [float("nan")] * (len(SHAPE_NAMES) - 2)
     rr, cc = np.nonzero(m)
-    rr = [int(v) for v in rr]
-    cc = [int(v) for v in cc]
-    bbox_area = float((max(rr) - min(rr) + 1) * (max(cc) - min(cc) + 1))
+    rr, cc = rr.astype(np.int64), cc.astype(np.int64)      # exact integer sums (< 2^63 for any plane)
+    bbox_area = float((int(rr.max()) - int(rr.min()) + 1) * (int(cc.max()) - int(cc.min()) + 1))
     extent = area / bbox_area
-    sr, sc = sum(rr), sum(cc)
-    srr = sum(v * v for v in rr)
-    scc = sum(v * v for v in cc)
-    src = sum(a_ * b_ for a_, b_ in zip(rr, cc))
+    sr, sc = int(rr.sum()), int(cc.sum())
+    srr, scc, src = int((rr * rr).sum()), int((cc * cc).sum()), int((rr * cc).sum())
     a2 = float(area) * float(area)
     a = float(area * scc - sc * sc) / a2            # mu02 / area  (column variance)
     c = float(area * srr - sr * sr) / a2            # mu20 / area  (row variance)

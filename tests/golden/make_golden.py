@@ -12,7 +12,7 @@ What it does: loads cell 13 of
 The numpy / scipy calls inside are the real libraries.  scikit-image is not installed
 here, so ``skimage.feature`` / ``skimage.measure`` are provided as stub modules backed
 by the restatements in ``oracle/notebook_oracle.py`` (validated against scikit-image's
-published known answers in tests/test_oracle_known_answers.py).  Consequently the
+published known answers in tests/test_oracle_cpu.py).  Consequently the
 17 basic columns of the fixture are reference-executed end to end; the 6 GLCM columns
 are reference control flow (quantiser, argument literals, key order) over restated
 skimage kernels.

@@ -59,6 +59,65 @@ def test_gather_table_gloo_world2(n_objects, chunk):
         assert shape == (n_objects, width)
 
 
+class _FakeExtractor:
+    """Stands in for FeatureExtractor on CPU tensors: row i of the table is a function of the object index
+    carried in planes[i, 0, 0]."""
+
+    def __init__(self, width):
+        self.width = width
+
+    def row_width(self, c):
+        return self.width
+
+    def extract_planar(self, planes, masks=None, sizes=None, hs=None, ws=None, out=None):
+        idx = planes[:, 0, 0].to(torch.float64)[:, None]
+        out.copy_(idx * 1000.0 + torch.arange(self.width, dtype=torch.float64)[None, :])
+        return out
+
+
+def _sharded_worker(rank, world, port, n_objects, width, slab, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        start, stop, per = D.shard_range(n_objects, world, rank)
+        planes = torch.arange(start, stop, dtype=torch.float64).reshape(-1, 1, 1)
+        tab = D.extract_sharded(_FakeExtractor(width), planes, n_objects=n_objects, slab_objects=slab)
+        ok = tab.transport == "collective" and bool(torch.equal(tab.table, _rows(0, n_objects, width)))
+        # the table object is reusable: a second extraction into the same buffers
+        tab2 = D.extract_sharded(_FakeExtractor(width), planes, n_objects=n_objects, slab_objects=slab, table=tab)
+        ok = ok and tab2 is tab and bool(torch.equal(tab.table, _rows(0, n_objects, width)))
+        q.put((rank, ok, tuple(tab.table.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_objects,slab", [(7, 2), (8, 4), (1, 16), (13, 3), (64, 64), (65, 16)])
+def test_extract_sharded_slab_pipeline_gloo_world2(n_objects, slab):
+    """The product's slab pipeline (kernels of slab k+1 while slab k is delivered) with the collective
+    transport on CPU tensors: every rank ends up with the full table, also with ragged last shards."""
+    world, width = 2, 23
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, n_objects, width, slab, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, shape in res:
+        assert ok, "rank %d assembled a wrong table" % rank
+        assert shape == (n_objects, width)
+
+
+def test_slab_bounds():
+    assert D.slab_bounds(0, 4) == []
+    assert D.slab_bounds(10, 4) == [(0, 4), (4, 8), (8, 10)]
+    assert D.slab_bounds(4, 100) == [(0, 4)]
+
+
 def test_shard_ranges_cover_everything():
     for n in (0, 1, 7, 8, 1000003):
         for world in (1, 2, 4, 8):

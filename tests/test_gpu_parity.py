@@ -56,13 +56,13 @@ def test_distributions_all_blocks(shape, torch_mod):
     got, status = imf.extract_features(img, four_directions=True, shape=True, moments=True,
                                        return_status=True)
     cols = imf.feature_columns(len(names), n_angles=4, shape=True, moments=True)
-    compare_tables(got, want, cols, label=str(shape))
+    compare_tables(got, want, cols, label=str(shape), images=img)
     if h * w > 1:
         assert status[0] & 4          # constant channels present
     # notebook-default call
     want = c_oracle.table(_planar(img))
     got = imf.extract_features(img)
-    compare_tables(got, want, imf.feature_columns(len(names)), label="default " + str(shape))
+    compare_tables(got, want, imf.feature_columns(len(names)), label="default " + str(shape), images=img)
 
 
 def test_against_numpy_oracle_directly(torch_mod):
@@ -72,7 +72,7 @@ def test_against_numpy_oracle_directly(torch_mod):
     img = np.stack([d[k] for k in sorted(d)], axis=2)
     want, cols = orc.oracle_extract([img], glcm=True, four_directions=True, shape=True, moments=True)
     got = imf.extract_features(img[None], four_directions=True, shape=True, moments=True)
-    compare_tables(got, want, cols, label="numpy oracle")
+    compare_tables(got, want, cols, label="numpy oracle", images=img[None])
 
 
 def test_glcm_bins_bit_exact(torch_mod):
@@ -120,7 +120,7 @@ def test_masked_all_blocks(shape, torch_mod):
     got, status = imf.extract_features(img, mask, four_directions=True, shape=True, moments=True,
                                        return_status=True)
     cols = imf.feature_columns(len(names), n_angles=4, shape=True, moments=True)
-    compare_tables(got, want, cols, label="masked " + str(shape))
+    compare_tables(got, want, cols, label="masked " + str(shape), images=img, masks=mask)
     assert status[0] & 1              # the empty mask was flagged
     # mask values other than 0/1 count as inside
     got2 = imf.extract_features(img, mask * 200, four_directions=True, shape=True, moments=True)
@@ -139,9 +139,9 @@ def test_variable_sizes(torch_mod):
     cols = imf.feature_columns(5, n_angles=4, shape=True, moments=True)
     for i, (o, m) in enumerate(zip(objs, masks)):
         want = c_oracle.table(_planar(o[None]), glcm=True, n_angles=4, shape=True, moments=True)
-        compare_tables(got[i:i + 1], want, cols, label="var %d %s" % (i, o.shape))
+        compare_tables(got[i:i + 1], want, cols, label="var %d %s" % (i, o.shape), images=[o])
         want = c_oracle.table(_planar(o[None]), _planar(m[None]), glcm=True, n_angles=4, shape=True, moments=True)
-        compare_tables(gotm[i:i + 1], want, cols, label="var masked %d %s" % (i, o.shape))
+        compare_tables(gotm[i:i + 1], want, cols, label="var masked %d %s" % (i, o.shape), images=[o], masks=[m])
 
 
 def test_odd_size_batch_uses_every_group(torch_mod):
