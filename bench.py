@@ -359,7 +359,7 @@ def run_b200(args):
                                "share": kms[k] / tot_k})
     dom = max(per_kernel, key=lambda d: d["share"])
     b_path = n_total * algorithmic_bytes_per_object(HS, WS, C, 1, F_FULL)
-    b_basic = n_total * algorithmic_bytes_per_object(HS, WS, C, 1, 17)
+    b_basic = n_obj * algorithmic_bytes_per_object(HS, WS, C, 1, 17)      # kernel times are per rank
     achieved = b_path / (ms_step * 1e-3) / 1e9
     traffic, tsrc = None, None
     tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")

@@ -8,8 +8,9 @@ the path is the gather of the per-rank row blocks (one all-gathe
 slab's rows straight into this rank's copy of the full table, and while the kernels of slab k+1 run,
 slab k travels to the other ranks on a side stream.  Two transports:
 
-  "p2p"         every rank maps the other ranks' tables through CUDA IPC and pushes its rows with plain
-                device-to-device copies: copy engines over NVLink, no SM is taken from the kernels
+  "p2p"         the tables are one symmetric-memory allocation (torch.distributed._symmetric_memory: every rank
+                has the other ranks' tables mapped into its own address space); a rank pushes its rows with
+                plain device-to-device copies: copy engines over NVLink, no SM is taken from the kernels
                 (an NCCL all-gather is an SM-resident kernel that competes with the persistent grids).
   "collective"  ``all_gather_into_tensor`` per slab (NCCL, or gloo on CPU tensors) -- the contract the
                 p2p transport is validated against, and the path the CPU tests exercise.
@@ -91,36 +92,31 @@ class ShardedTable:
         dtype = torch.float64 if dtype is None else dtype
         self.device = torch.device("cpu") if device is None else torch.device(device)
         self.cuda = self.device.type == "cuda"
-        self.full = torch.zeros((self.world * self.per, self.width), dtype=dtype, device=self.device)
         if transport is None:
             transport = "p2p" if (self.cuda and self.world > 1) else "collective"
         self.transport = transport
         self.side = torch.cuda.Stream(device=self.device) if self.cuda else None
         self.peers = None
+        self.full = None
         self._stage = {}
         self._n_push = 0
+        shape = (self.world * self.per, self.width)
         if self.transport == "p2p":
             try:
-                self._map_peers()
-            except Exception as exc:                       # no IPC on this box / allocator: the collective still works
-                self.transport, self.fallback_reason = "collective", repr(exc)
-                ok = torch.zeros(1, device=self.device)
-            else:
-                ok = torch.ones(1, device=self.device)
-            # every rank must use the same transport
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-            if float(ok.item()) == 0.0:
-                self.transport, self.peers = "collective", None
+                self._map_peers(shape, dtype)
+            except Exception as exc:                       # no symmetric memory on this box: the collective still works
+                self.transport, self.fallback_reason, self.peers, self.full = "collective", repr(exc), None, None
+        if self.full is None:
+            self.full = torch.zeros(shape, dtype=dtype, device=self.device)
 
-    def _map_peers(self):
-        """Exchange CUDA IPC handles of the tables: peers[r] is rank r's table, mapped into this process."""
-        from torch.multiprocessing.reductions import reduce_tensor
-        fn, args = reduce_tensor(self.full)
-        handles = [None] * self.world
-        self.dist.all_gather_object(handles, (fn, args), group=self.group)
-        self.peers = []
-        for r, (f, a) in enumerate(handles):
-            self.peers.append(self.full if r == self.rank else f(*a))
+    def _map_peers(self, shape, dtype):
+        """One symmetric allocation: peers[r] is rank r's table, mapped into this rank's address space."""
+        import torch.distributed._symmetric_memory as symm
+        grp = self.group if self.group is not None else self.dist.group.WORLD
+        self.full = symm.empty(shape, dtype=dtype, device=self.device)
+        self.full.zero_()
+        self._handle = symm.rendezvous(self.full, grp)
+        self.peers = [self.full if r == self.rank else self._handle.get_buffer(r, shape, dtype) for r in range(self.world)]
 
     @property
     def table(self):
