@@ -95,6 +95,27 @@ def load(build_if_missing=True):
     return L
 
 
+_TORCH_OPS = None
+
+
+def load_torch_ops(build_if_missing=True):
+    """Load the thin PyTorch C++ extension (csrc_torch/imfeat_torch.cpp -> libimfeat_torch.so) that registers
+    ``torch.ops.imfeat.extract`` / ``glcm_counts`` / ``row_width`` over the same C ABI.  Raises if it is missing."""
+    global _TORCH_OPS
+    if _TORCH_OPS is not None:
+        return _TORCH_OPS
+    import torch
+    load(build_if_missing)
+    path = _build.TORCH_EXT_PATH
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise ImfeatError("torch extension %s is missing (run __graft_entry__.build())" % path)
+        _build.build_torch_extension()
+    torch.ops.load_library(path)
+    _TORCH_OPS = torch.ops.imfeat
+    return _TORCH_OPS
+
+
 def check(rc, ctx=None):
     if rc != 0:
         msg = load().imfeat_last_error(ctx)

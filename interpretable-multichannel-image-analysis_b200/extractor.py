@@ -155,10 +155,22 @@ class FeatureExtractor:
         assert out.is_cuda and out.dtype == torch.float64 and out.stride(1) == 1
         for idx in (sizes, src_obj, chan):
             assert idx is None or (idx.is_cuda and idx.dtype == torch.int32 and idx.is_contiguous())
-        _lib.check(self.lib.imfeat_extract_device(
-            self._ctx, _ptr(planes), _ptr(masks), _ptr(sizes), _ptr(src_obj), _ptr(chan), N, C,
-            c_out, hs, ws, stride, ctypes.byref(self.opts), _ptr(out), int(out.stride(0)),
-            _ptr(status), self._stream(stream)), self._ctx)
+        # through the torch op (csrc_torch/imfeat_torch.cpp): tensors in, current stream taken from torch
+        ops = _lib.load_torch_ops()
+        o = self.opts
+        args = (planes.view(torch.int16) if planes.dtype != torch.int16 else planes,
+                None if masks is None else masks.view(torch.uint8).reshape(N, C, stride), sizes, src_obj, chan, int(hs), int(ws),
+                bool(o.want_basic), bool(o.want_glcm), int(o.n_angles), int(o.glcm_distance), bool(o.want_shape),
+                bool(o.want_moments), [float(q) for q in o.percentiles], out,
+                None if status is None else status.view(torch.int32), int(self._ctx.value))
+        try:
+            if stream is None:
+                ops.extract(*args)
+            else:
+                with torch.cuda.stream(stream):
+                    ops.extract(*args)
+        except RuntimeError as exc:                        # TORCH_CHECK (shape / dtype / device misuse) or a C-ABI error
+            raise _lib.ImfeatError(str(exc).split("\n")[0]) from None
         return out
 
     def pack_hwc(self, images, masks=None, sizes=None, stream=None):
@@ -185,11 +197,14 @@ class FeatureExtractor:
             if masks is not None and masks.dim() == 4:
                 masks = _planes3(masks)[0]
         N, C, stride = (int(v) for v in planes.shape)
-        counts = torch.empty((N, C, self.n_angles, 256, 256), dtype=torch.int32, device=planes.device)
-        _lib.check(self.lib.imfeat_glcm_counts_device(
-            self._ctx, _ptr(planes), _ptr(masks), _ptr(sizes), N, C, hs, ws, stride,
-            ctypes.byref(self.opts), _ptr(counts), self._stream(stream)), self._ctx)
-        return counts
+        ops = _lib.load_torch_ops()
+        args = (planes.view(torch.int16) if planes.dtype != torch.int16 else planes,
+                None if masks is None else masks.view(torch.uint8).reshape(N, C, stride), sizes, int(hs), int(ws),
+                int(self.n_angles), int(self.opts.glcm_distance), int(self._ctx.value))
+        if stream is None:
+            return ops.glcm_counts(*args)
+        with torch.cuda.stream(stream):
+            return ops.glcm_counts(*args)
 
     def synth(self, seed, first, count, c, hs, ws, with_masks=True, variable=False, hmin=1, wmin=1,
               mask_shrink=256, stream=None):

@@ -31,6 +31,28 @@ def test_library_builds_and_exports_header_symbols():
     assert L.imfeat_abi_version() == 1
 
 
+def test_torch_extension_builds_and_registers_the_ops():
+    """The thin PyTorch C++ extension over the C ABI (north_star: "calls CUDA through a thin PyTorch C++/CUDA
+    extension"): builds with g++, loads, and registers imfeat::extract / glcm_counts / row_width with the
+    schema SURVEY 8(b) sketches.  No compute call without a GPU."""
+    import torch
+    from imfeat_b200 import _lib, build
+    path = build.build_torch_extension()
+    assert os.path.exists(path)
+    ops = _lib.load_torch_ops()
+    schema = str(torch.ops.imfeat.extract.default._schema)
+    for piece in ("Tensor planes", "Tensor? masks", "Tensor? sizes", "Tensor? src_obj", "Tensor? chan", "float[] percentiles",
+                  "int ctx=0", "-> Tensor"):
+        assert piece in schema, schema
+    assert "Tensor planes" in str(torch.ops.imfeat.glcm_counts.default._schema)
+    assert ops.row_width(3, True, True, 1, False, False) == 69                          # NB:317
+    assert ops.row_width(12, True, True, 4, True, True) == 720
+    if not torch.cuda.is_available():
+        with pytest.raises((RuntimeError, NotImplementedError)):                        # no CPU kernel is registered
+            ops.extract(torch.zeros((1, 1, 64), dtype=torch.int16), None, None, None, None, 8, 8, True, True, 1, 5,
+                        False, False, [], None, None, 0)
+
+
 def test_default_opts_are_the_notebook_literals():
     from imfeat_b200 import _lib
     L = _lib.load()

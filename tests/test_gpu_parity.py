@@ -294,6 +294,33 @@ def test_full_size_properties(torch_mod):
                     for i in pick])
     want = c_oracle.table(_planar(img), glcm=True, n_angles=4)
     compare_tables(t[pick], want, cols, label="1024 sampled objects")
+    # the same at the headline configuration: masks, four directions, shape, moments (every kernel's masked variant)
+    exf = imf.get_extractor(four_directions=True, shape=True, moments=True)
+    tm = exf.extract_planar(planes, masks, hs=64, ws=64).cpu().numpy()
+    mk = np.stack([np.stack([synth.synth_plane(0, int(i), ch, 64, 64)[1] for ch in range(C)], axis=2) for i in pick])
+    want = c_oracle.table(_planar(img), _planar(mk), glcm=True, n_angles=4, shape=True, moments=True)
+    compare_tables(tm[pick], want, exf.columns(C), label="1024 sampled objects, masked, all blocks", images=img, masks=mk)
+
+
+def test_cfg5_shaped_batch(torch_mod):
+    """BASELINE.json configs[4]: variable-size objects up to 128x128, 18 channels, sparse masks (1-10% of the tile),
+    fixed stride with a size table, every block, device-generated and checked against the C oracle object by object."""
+    from imfeat_b200 import synth
+    ex = imf.get_extractor(four_directions=True, shape=True, moments=True)
+    N, C5 = 96, 18
+    planes, masks, sizes = ex.synth(5, 0, N, C5, 128, 128, with_masks=True, variable=True, hmin=16, wmin=16, mask_shrink=32)
+    got = ex.extract_planar(planes, masks, sizes, hs=128, ws=128).cpu().numpy()
+    cols = ex.columns(C5)
+    frac = []
+    for i in range(N):
+        h, w = synth.object_size(5, i, 128, 128, True, 16, 16)
+        pl = [synth.synth_plane(5, i, ch, h, w, mask_shrink=32) for ch in range(C5)]
+        img = np.stack([p[0] for p in pl], axis=2)[None]
+        mk = np.stack([p[1] for p in pl], axis=2)[None]
+        frac.append(mk.mean())
+        want = c_oracle.table(_planar(img), _planar(mk), glcm=True, n_angles=4, shape=True, moments=True)
+        compare_tables(got[i:i + 1], want, cols, label="cfg5 object %d (%dx%d)" % (i, h, w), images=img, masks=mk)
+    assert 0.01 < np.mean(frac) < 0.10
 
 
 def test_custom_percentiles_and_distance(torch_mod):
@@ -412,6 +439,67 @@ def test_repeatability(torch_mod):
     torch.cuda.synchronize()
     assert torch.equal(a.view(torch.int64), b.view(torch.int64))
     assert torch.equal(a.view(torch.int64), c.view(torch.int64))
+
+
+def test_torch_ops_direct(torch_mod):
+    """torch.ops.imfeat.extract / glcm_counts called directly (context kept by the extension, current stream from
+    torch) give the same bits as the FeatureExtractor route, also under CUDA-graph capture."""
+    torch = torch_mod
+    from imfeat_b200 import _lib
+    ops = _lib.load_torch_ops()
+    ex = imf.get_extractor(four_directions=True, shape=True, moments=True)
+    planes, masks, _ = ex.synth(8, 0, 64, 5, 64, 64)
+    want = ex.extract_planar(planes, masks, hs=64, ws=64)
+    p16 = planes.view(torch.int16)
+    got = ops.extract(p16, masks, None, None, None, 64, 64, True, True, 4, 5, True, True, [], None, None)
+    assert torch.equal(got.view(torch.int64), want.view(torch.int64))
+    chan = torch.tensor([4, 0, 2], dtype=torch.int32, device=planes.device)
+    sub = ops.extract(p16, masks, None, None, chan, 64, 64, True, False, 1, 5, False, False, [], None, None)
+    exb = imf.get_extractor(glcm=False)
+    assert torch.equal(sub.view(torch.int64), exb.extract_planar(planes, masks, hs=64, ws=64, chan=chan).view(torch.int64))
+    c1 = ops.glcm_counts(p16, masks, None, 64, 64, 4, 5)
+    assert torch.equal(c1, imf.get_extractor(four_directions=True).glcm_counts(planes, masks, hs=64, ws=64))
+    out = torch.empty_like(want)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ops.extract(p16, masks, None, None, None, 64, 64, True, True, 4, 5, True, True, [], out, None)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int64), want.view(torch.int64))
+
+
+def test_repeatability_all_paths(torch_mod):
+    """Stand-in for compute-sanitizer's racecheck (closed on this pool, profiles/r2_sanitizer_note.txt): a batch that
+    takes every kernel path -- histogram window hit and miss, full-range ring, FP64 moments, 4-bit and 8-bit GLCM
+    tables with wrapped counters and their fallbacks, the unmasked ring kernel -- repeated 25 times must give the
+    same bits every time, tables and raw GLCM bins alike.  A shared-memory race shows up as a run-to-run difference."""
+    torch = torch_mod
+    rng = np.random.default_rng(0)
+    n, h, w, c = 96, 64, 64, 4
+    img = rng.integers(100, 3000, (n, h, w, c)).astype(np.uint16)
+    img[:, :, :, 1] = rng.integers(0, 65536, (n, h, w))
+    img[:, :, :, 2] = rng.choice([7, 7, 7, 900], (n, h, w))
+    mask = (rng.random((n, h, w, c)) < 0.6).astype(np.uint8)
+    mask[:, :, :, 2] = 1
+    planes = torch.from_numpy(_planar(img)).cuda()
+    masks = torch.from_numpy(_planar(mask)).cuda()
+    exf = imf.get_extractor(four_directions=True, shape=True, moments=True)
+    exn = imf.get_extractor()
+    exg = imf.get_extractor(four_directions=True)
+    ref = None
+    for rep in range(25):
+        cur = (exf.extract_planar(planes, masks).view(torch.int64).clone(),
+               exn.extract_planar(planes, None).view(torch.int64).clone(),
+               exg.glcm_counts(planes[:8], masks[:8]).clone(), exg.glcm_counts(planes[:8]).clone())
+        if ref is None:
+            ref = cur
+        else:
+            for k, (a, b) in enumerate(zip(ref, cur)):
+                assert torch.equal(a, b), "repetition %d differs in result %d" % (rep, k)
+    want = c_oracle.table(_planar(img), _planar(mask), glcm=True, n_angles=4, shape=True, moments=True)
+    compare_tables(ref[0].view(torch.float64).cpu().numpy(), want, exf.columns(c), label="all paths", images=img, masks=mask)
 
 
 def test_pinned_batcher_end_to_end(torch_mod):
