@@ -339,6 +339,19 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * n_e2e / e2e_s
+    # the same call with the masks in the bit-packed host format (packed once, outside the timed region)
+    h_bits = torch.from_numpy(imf.pack_mask_bits(h_mask)).pin_memory().numpy()
+    ex.extract_host_hwc(h_img, h_bits, out=h_out, masks_packed=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ex.extract_host_hwc(h_img, h_bits, out=h_out, masks_packed=True)
+    torch.cuda.synchronize()
+    e2e_bits_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_bits_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_bits_s = float(t.item())
     dev_rows = out[:n_e2e] if world == 1 else table.table[first:first + n_e2e]
     assert np.array_equal(h_out, dev_rows.cpu().numpy(), equal_nan=True), "host and device paths disagree"
 
@@ -401,6 +414,10 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_img.nbytes + h_mask.nbytes),
                 "d2h_bytes_per_step": int(h_out.nbytes), "objects_per_gpu": int(n_e2e),
                 "call": "FeatureExtractor.extract_host_hwc -> imfeat_extract_host_hwc (pinned host buffers, README (h,w,c) layout)"},
+        "e2e_bitmask": {"value": world * n_e2e / e2e_bits_s, "unit": UNIT, "h2d_bytes_per_step": int(h_img.nbytes + h_bits.nbytes),
+                        "d2h_bytes_per_step": int(h_out.nbytes),
+                        "call": "the same call with the masks in the bit-packed host format (opts.host_mask_bits; imfeat_b200.pack_mask_bits): "
+                                "a byte mask is a third of the PCIe traffic of an object, a packed one 4%; expanded to bytes on the device"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "whole step (every kernel of one extraction); dominant: " + dom["kernel"],

@@ -74,7 +74,7 @@ typedef struct imfeat_opts {
     int32_t glcm_distance;        /* notebook literal: 5 (NB:298)                           */
     int32_t want_shape;           /* extension                                              */
     int32_t want_moments;         /* extension                                              */
-    int32_t reserved;
+    int32_t host_mask_bits;       /* host entry points only: 1 = h_masks is bit-packed (see below)      */
     double percentiles[9];        /* np.percentile q arguments; notebook: 0.1 .. 0.9        */
 } imfeat_opts;
 
@@ -125,7 +125,15 @@ int imfeat_extract_host(imfeat_ctx *ctx, const uint16_t *h_planes, const uint8_t
  * when h_sizes is given.  The interleaved slab is copied to the device as is and converted to
  * the planar layout there (imfeat_pack_hwc_device), so the host never transposes pixels.
  * This is the call that replaces the whole loop body NB:358-364 for a batch of objects.
+ *
+ * Bit-packed host masks (opts->host_mask_bits = 1, both host entry points): the masks are a third of the bytes
+ * that cross PCIe; packed they are 4%.  Element k of an object (imfeat_extract_host_hwc: k = (r*ws + col)*c + ch
+ * over the padded hs x ws x c block) or of a plane (imfeat_extract_host: k = index inside the plane's
+ * plane_stride elements) is bit k & 7 of byte k >> 3 (numpy.packbits(..., bitorder="little")); every object /
+ * plane starts at a multiple of 8 bytes: IMFEAT_MASK_BITS_BYTES(n_elements) bytes each.  The masks are
+ * expanded to bytes on the device.
  */
+#define IMFEAT_MASK_BITS_BYTES(n_elements) ((((int64_t)(n_elements) + 63) / 64) * 8)
 int imfeat_extract_host_hwc(imfeat_ctx *ctx, const uint16_t *h_hwc, const uint8_t *h_mask_hwc,
                             const int32_t *h_sizes, int64_t n_objects, int32_t c, int32_t hs,
                             int32_t ws, const imfeat_opts *opts, double *h_out,

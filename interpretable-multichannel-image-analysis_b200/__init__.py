@@ -10,11 +10,11 @@ from .batcher import PinnedBatcher
 from .postprocess import MinMaxScaler
 from ._lib import ImfeatError
 from .extractor import (FeatureExtractor, basic_statistical_features, extract_features, from_unit_float,
-                        get_extractor, glcm_features, plane_stride_for)
+                        get_extractor, glcm_features, pack_mask_bits, plane_stride_for)
 from .schema import feature_columns
 
 __all__ = [
     "FeatureExtractor", "ImfeatError", "basic_statistical_features", "extract_features",
-    "feature_columns", "from_unit_float", "get_extractor", "glcm_features", "plane_stride_for", "schema",
+    "feature_columns", "from_unit_float", "get_extractor", "glcm_features", "pack_mask_bits", "plane_stride_for", "schema",
     "ablation", "batcher", "distributed", "postprocess", "synth", "PinnedBatcher", "MinMaxScaler",
 ]

@@ -20,7 +20,7 @@ class ImfeatOpts(ctypes.Structure):
         ("glcm_distance", ctypes.c_int32),
         ("want_shape", ctypes.c_int32),
         ("want_moments", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("host_mask_bits", ctypes.c_int32),
         ("percentiles", ctypes.c_double * 9),
     ]
 

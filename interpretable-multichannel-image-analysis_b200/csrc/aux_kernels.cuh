@@ -8,11 +8,14 @@ namespace imfeat {
 // interleaved batch uint16[N][hs][ws][c] to the plane-compact planar layout.  One thread per
 // valid pixel reads its c interleaved samples (contiguous) and scatters them to c planes
 // (each store coalesced across the warp).
+// mask_bits != 0: mhwc is bit-packed, bit k of an object = element k of its padded (hs, ws, c) block, every
+// object starting at a multiple of 8 bytes (include/imfeat.h, IMFEAT_MASK_BITS_BYTES).
 __global__ void pack_hwc_kernel(const uint16_t* __restrict__ hwc, const uint8_t* __restrict__ mhwc,
                                 const int32_t* __restrict__ sizes, long long n_objects, int c,
                                 int hs, int ws, long long plane_stride,
-                                uint16_t* __restrict__ planes, uint8_t* __restrict__ masks) {
+                                uint16_t* __restrict__ planes, uint8_t* __restrict__ masks, int mask_bits) {
     const long long per_obj = (long long)hs * ws;
+    const long long obj_bits_bytes = ((per_obj * c + 63) / 64) * 8;
     const long long total = n_objects * per_obj;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
          g += (long long)gridDim.x * blockDim.x) {
@@ -25,8 +28,28 @@ __global__ void pack_hwc_kernel(const uint16_t* __restrict__ hwc, const uint8_t*
         const long long dst = obj * c * plane_stride + (long long)r * w + col;
         for (int ch = 0; ch < c; ++ch) {
             planes[dst + ch * plane_stride] = hwc[src + ch];
-            if (masks) masks[dst + ch * plane_stride] = mhwc[src + ch];
+            if (masks) {
+                if (mask_bits) {
+                    const long long k = (long long)pix * c + ch;
+                    masks[dst + ch * plane_stride] = (mhwc[obj * obj_bits_bytes + (k >> 3)] >> (k & 7)) & 1;
+                } else {
+                    masks[dst + ch * plane_stride] = mhwc[src + ch];
+                }
+            }
         }
+    }
+}
+
+// Bit-packed planar masks -> byte masks: one thread per 8 elements (one packed byte -> one 64-bit store).
+__global__ void unpack_mask_bits_kernel(const uint8_t* __restrict__ bits, long long n_planes, long long plane_stride,
+                                        uint8_t* __restrict__ masks) {
+    const long long plane_bits_bytes = ((plane_stride + 63) / 64) * 8, groups = plane_stride >> 3;   // plane_stride % 8 == 0
+    const long long total = n_planes * groups;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const long long pl = g / groups, k = g - pl * groups;
+        const uint32_t b = bits[pl * plane_bits_bytes + k];
+        const uint32_t lo = ((b & 0xfu) * 0x00204081u) & 0x01010101u, hi = (((b >> 4) & 0xfu) * 0x00204081u) & 0x01010101u;
+        reinterpret_cast<uint2*>(masks + pl * plane_stride)[k] = make_uint2(lo, hi);
     }
 }
 

@@ -698,7 +698,7 @@ int imfeat_pack_hwc_device(imfeat_ctx* ctx, const uint16_t* d_hwc, const uint8_t
     const long long want = (total + 255) / 256;
     const int grid = (int)(want < (long long)ctx->sm_count * 16 ? want : (long long)ctx->sm_count * 16);
     pack_hwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_hwc, d_mask_hwc, d_sizes, n_objects, c, hs,
-                                                           ws, plane_stride, d_planes, d_masks);
+                                                           ws, plane_stride, d_planes, d_masks, 0);
     ctx->launches += 1;
     CU(cudaGetLastError());
     return IMFEAT_OK;
@@ -761,14 +761,21 @@ static int extract_host_impl(imfeat_ctx* ctx, int layout, const uint16_t* h_img,
     }
     const size_t src_px = layout ? (size_t)hs * ws * c : (size_t)c * plane_stride;  // host elems/object
     const size_t pl_px = (size_t)c * plane_stride;                                  // planar elems/object
-    const size_t obj_in = src_px * 2 + (h_masks ? src_px : 0) + 8 +
-                          (layout ? pl_px * 2 + (h_masks ? pl_px : 0) : 0);
+    // host mask bytes per object: one per element, or bit-packed (every object / plane padded to 8 bytes)
+    const bool mbits = h_masks && opts->host_mask_bits != 0;
+    const size_t src_mk = !h_masks ? 0 : !mbits ? src_px
+                        : layout ? (size_t)IMFEAT_MASK_BITS_BYTES(src_px) : (size_t)c * (size_t)IMFEAT_MASK_BITS_BYTES(plane_stride);
+    const bool planar_copy_px = layout != 0;                 // interleaved pixels are packed to planes on the device
+    const bool planar_copy_mk = h_masks && (layout != 0 || mbits);
+    const size_t obj_in = src_px * 2 + src_mk + 8 + (planar_copy_px ? pl_px * 2 : 0) + (planar_copy_mk ? pl_px : 0);
     const size_t obj_out = (size_t)width * 8 + 4;
     int64_t slab = (int64_t)(((size_t)64 << 20) / (src_px * 2));      // ~64 MiB of pixels per slab
     if (slab < 1) slab = 1;
     if (slab > n_objects) slab = n_objects;
     const size_t need_in = (size_t)slab * obj_in + 256, need_out = (size_t)slab * obj_out + 64;
     if (need_in > ctx->in_bytes || need_out > ctx->out_bytes) {
+        // nobody else may still use the old staging buffers: the two host-path streams are drained first
+        for (int b = 0; b < 2; ++b) CU(cudaStreamSynchronize(ctx->streams[b]));
         free_staging(ctx);
         for (int b = 0; b < 2; ++b) {
             CU(cudaMallocHost(&ctx->pin_in[b], need_in));
@@ -780,15 +787,18 @@ static int extract_host_impl(imfeat_ctx* ctx, int layout, const uint16_t* h_img,
         ctx->out_bytes = need_out;
     }
     const bool direct_in = is_pinned(h_img) && (!h_masks || is_pinned(h_masks));
+    // results go straight into the caller's buffer when it is pinned and dense (no staging copy on the host)
+    const bool direct_out = row_stride == width && is_pinned(h_out) && (!h_status || is_pinned(h_status));
     const int64_t n_slabs = (n_objects + slab - 1) / slab;
     // byte offsets inside a slab buffer: [pixels | masks | sizes | planar pixels | planar masks]
     auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     const size_t off_mask = up16((size_t)slab * src_px * 2);
-    const size_t off_size = up16(off_mask + (h_masks ? (size_t)slab * src_px : 0));
+    const size_t off_size = up16(off_mask + (size_t)slab * src_mk);
     const size_t off_plpx = up16(off_size + (size_t)slab * 8);
-    const size_t off_plmk = up16(off_plpx + (layout ? (size_t)slab * pl_px * 2 : 0));
+    const size_t off_plmk = up16(off_plpx + (planar_copy_px ? (size_t)slab * pl_px * 2 : 0));
     const size_t off_stat = (size_t)slab * width * 8;
     auto drain = [&](int64_t s) {   // copy slab s's results from pinned staging to the caller
+        if (direct_out) return;
         const int b = (int)(s & 1);
         const int64_t first = s * slab, cnt = (first + slab <= n_objects) ? slab : n_objects - first;
         const double* src = (const double*)ctx->pin_out[b];
@@ -804,16 +814,16 @@ static int extract_host_impl(imfeat_ctx* ctx, int layout, const uint16_t* h_img,
         char* din = (char*)ctx->dev_in[b];
         char* pin = (char*)ctx->pin_in[b];
         const uint16_t* src_img = h_img + (size_t)first * src_px;
-        const uint8_t* src_mk = h_masks ? h_masks + (size_t)first * src_px : nullptr;
+        const uint8_t* src_mask = h_masks ? h_masks + (size_t)first * src_mk : nullptr;
         if (direct_in) {
             CU(cudaMemcpyAsync(din, src_img, (size_t)cnt * src_px * 2, cudaMemcpyHostToDevice, st));
-            if (h_masks) CU(cudaMemcpyAsync(din + off_mask, src_mk, (size_t)cnt * src_px, cudaMemcpyHostToDevice, st));
+            if (h_masks) CU(cudaMemcpyAsync(din + off_mask, src_mask, (size_t)cnt * src_mk, cudaMemcpyHostToDevice, st));
         } else {
             memcpy(pin, src_img, (size_t)cnt * src_px * 2);
             CU(cudaMemcpyAsync(din, pin, (size_t)cnt * src_px * 2, cudaMemcpyHostToDevice, st));
             if (h_masks) {
-                memcpy(pin + off_mask, src_mk, (size_t)cnt * src_px);
-                CU(cudaMemcpyAsync(din + off_mask, pin + off_mask, (size_t)cnt * src_px, cudaMemcpyHostToDevice, st));
+                memcpy(pin + off_mask, src_mask, (size_t)cnt * src_mk);
+                CU(cudaMemcpyAsync(din + off_mask, pin + off_mask, (size_t)cnt * src_mk, cudaMemcpyHostToDevice, st));
             }
         }
         if (h_sizes) {
@@ -824,11 +834,20 @@ static int extract_host_impl(imfeat_ctx* ctx, int layout, const uint16_t* h_img,
         const uint16_t* d_planes = (const uint16_t*)din;
         const uint8_t* d_masks = h_masks ? (const uint8_t*)(din + off_mask) : nullptr;
         if (layout) {
-            rc = imfeat_pack_hwc_device(ctx, (const uint16_t*)din, d_masks, d_sizes, cnt, c, hs, ws, plane_stride,
-                                        (uint16_t*)(din + off_plpx), h_masks ? (uint8_t*)(din + off_plmk) : nullptr, st);
-            if (rc) return rc;
+            const long long total = (long long)cnt * hs * ws, want = (total + 255) / 256;
+            const int grid = (int)(want < (long long)ctx->sm_count * 16 ? want : (long long)ctx->sm_count * 16);
+            pack_hwc_kernel<<<grid, 256, 0, st>>>((const uint16_t*)din, d_masks, d_sizes, cnt, c, hs, ws, plane_stride,
+                                                  (uint16_t*)(din + off_plpx), h_masks ? (uint8_t*)(din + off_plmk) : nullptr,
+                                                  mbits ? 1 : 0);
+            ctx->launches += 1;
             d_planes = (const uint16_t*)(din + off_plpx);
             d_masks = h_masks ? (const uint8_t*)(din + off_plmk) : nullptr;
+        } else if (mbits) {
+            const long long total = (long long)cnt * c * (plane_stride >> 3), want = (total + 255) / 256;
+            const int grid = (int)(want < (long long)ctx->sm_count * 16 ? want : (long long)ctx->sm_count * 16);
+            unpack_mask_bits_kernel<<<grid, 256, 0, st>>>(d_masks, (long long)cnt * c, plane_stride, (uint8_t*)(din + off_plmk));
+            ctx->launches += 1;
+            d_masks = (const uint8_t*)(din + off_plmk);
         }
         double* dout = (double*)ctx->dev_out[b];
         uint32_t* dstat = (uint32_t*)((char*)ctx->dev_out[b] + off_stat);
@@ -838,8 +857,13 @@ static int extract_host_impl(imfeat_ctx* ctx, int layout, const uint16_t* h_img,
                     opts, dout, width, dstat);
         rc = launch_all(ctx, P, opts, st);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(ctx->pin_out[b], dout, (size_t)cnt * width * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync((char*)ctx->pin_out[b] + off_stat, dstat, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        if (direct_out) {
+            CU(cudaMemcpyAsync(h_out + first * row_stride, dout, (size_t)cnt * width * 8, cudaMemcpyDeviceToHost, st));
+            if (h_status) CU(cudaMemcpyAsync(h_status + first, dstat, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        } else {
+            CU(cudaMemcpyAsync(ctx->pin_out[b], dout, (size_t)cnt * width * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync((char*)ctx->pin_out[b] + off_stat, dstat, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        }
         CU(cudaEventRecord(ctx->done[b], st));
     }
     for (int64_t s = (n_slabs >= 2 ? n_slabs - 2 : 0); s < n_slabs; ++s) {

@@ -40,6 +40,19 @@ def plane_stride_for(hs, ws):
     return (hs * ws + 7) & ~7
 
 
+def pack_mask_bits(masks):
+    """uint8/bool masks [N, ...] -> the bit-packed host format of the C ABI (include/imfeat.h, host_mask_bits):
+    element k of an object is bit k & 7 of byte k >> 3, every object padded to a multiple of 8 bytes.  A mask is a
+    third of the bytes that cross PCIe per object; packed it is 4 %."""
+    m = np.asarray(masks)
+    n = m.shape[0]
+    bits = np.packbits(m.reshape(n, -1) != 0, axis=1, bitorder="little")
+    want = ((m[0].size + 63) // 64) * 8 if n else 0
+    if bits.shape[1] != want:
+        bits = np.concatenate([bits, np.zeros((n, want - bits.shape[1]), np.uint8)], axis=1)
+    return np.ascontiguousarray(bits)
+
+
 def _planes3(t):
     """[N, C, Hs, Ws] -> ([N, C, plane_stride], hs, ws); pads the plane to a multiple of 8
     elements when Hs*Ws is not one (the C ABI wants 16-byte aligned planes)."""
@@ -223,13 +236,20 @@ class FeatureExtractor:
         return planes, masks, sizes
 
     # -- host buffers (the reference-facing call) ----------------------------------------------
-    def extract_host_hwc(self, images, masks=None, sizes=None, out=None, return_status=False):
-        """images: numpy uint16 [N, hs, ws, C] (pinned or pageable), masks uint8 same shape,
-        sizes int32 [N, 2] or None.  Returns numpy float64 [N, row_width]."""
+    def extract_host_hwc(self, images, masks=None, sizes=None, out=None, return_status=False, masks_packed=False):
+        """images: numpy uint16 [N, hs, ws, C] (pinned or pageable), masks uint8 same shape -- or, with
+        masks_packed=True, the bit-packed form ``pack_mask_bits`` returns --, sizes int32 [N, 2] or None.
+        Returns numpy float64 [N, row_width]."""
         images = np.ascontiguousarray(images)
         assert images.dtype == np.uint16 and images.ndim == 4
         N, hs, ws, C = images.shape
-        if masks is not None:
+        opts = self.opts
+        if masks is not None and masks_packed:
+            masks = np.ascontiguousarray(masks)
+            assert masks.dtype == np.uint8 and masks.shape == (N, ((hs * ws * C + 63) // 64) * 8)
+            opts = _lib.ImfeatOpts.from_buffer_copy(self.opts)
+            opts.host_mask_bits = 1
+        elif masks is not None:
             masks = np.ascontiguousarray(masks)
             if masks.dtype == np.bool_:
                 masks = masks.view(np.uint8)
@@ -243,13 +263,14 @@ class FeatureExtractor:
         status = np.zeros(N, dtype=np.uint32) if return_status else None
         _lib.check(self.lib.imfeat_extract_host_hwc(
             self._ctx, _np_ptr(images), _np_ptr(masks), _np_ptr(sizes), N, C, hs, ws,
-            ctypes.byref(self.opts), _np_ptr(out), int(out.strides[0] // 8), _np_ptr(status)),
+            ctypes.byref(opts), _np_ptr(out), int(out.strides[0] // 8), _np_ptr(status)),
             self._ctx)
         return (out, status) if return_status else out
 
     def extract_host_planar(self, planes, masks=None, sizes=None, hs=None, ws=None,
-                            return_status=False):
-        """planes: numpy uint16 [N, C, Hs, Ws] or [N, C, plane_stride] (give hs, ws)."""
+                            return_status=False, masks_packed=False):
+        """planes: numpy uint16 [N, C, Hs, Ws] or [N, C, plane_stride] (give hs, ws); masks the same shape, or
+        with masks_packed=True ``pack_mask_bits(masks.reshape(N * C, -1))`` (every plane packed on its own)."""
         planes = np.ascontiguousarray(planes)
         assert planes.dtype == np.uint16
         N, C = planes.shape[:2]
@@ -258,7 +279,13 @@ class FeatureExtractor:
             stride = hs * ws
         else:
             stride = planes.shape[2]
-        if masks is not None:
+        opts = self.opts
+        if masks is not None and masks_packed:
+            masks = np.ascontiguousarray(masks)
+            assert masks.dtype == np.uint8 and masks.size == N * C * ((stride + 63) // 64) * 8
+            opts = _lib.ImfeatOpts.from_buffer_copy(self.opts)
+            opts.host_mask_bits = 1
+        elif masks is not None:
             masks = np.ascontiguousarray(masks).view(np.uint8)
         if sizes is not None:
             sizes = np.ascontiguousarray(sizes, dtype=np.int32)
@@ -267,7 +294,7 @@ class FeatureExtractor:
         status = np.zeros(N, dtype=np.uint32) if return_status else None
         _lib.check(self.lib.imfeat_extract_host(
             self._ctx, _np_ptr(planes), _np_ptr(masks), _np_ptr(sizes), N, C, hs, ws, stride,
-            ctypes.byref(self.opts), _np_ptr(out), width, _np_ptr(status)), self._ctx)
+            ctypes.byref(opts), _np_ptr(out), width, _np_ptr(status)), self._ctx)
         return (out, status) if return_status else out
 
 

@@ -441,6 +441,34 @@ def test_repeatability(torch_mod):
     assert torch.equal(a.view(torch.int64), c.view(torch.int64))
 
 
+def test_bit_packed_host_masks(torch_mod):
+    """Host entry points with bit-packed masks (opts.host_mask_bits): same bits as with byte masks, for the
+    interleaved (h, w, c) layout with a size table and for the planar layout, pinned and pageable buffers."""
+    torch = torch_mod
+    rng = np.random.default_rng(9)
+    n, h, w, c = 37, 37, 53, 3                      # 37*53*3 and the plane stride are no multiples of 64
+    img = rng.integers(0, 4096, (n, h, w, c)).astype(np.uint16)
+    mask = (rng.random((n, h, w, c)) < 0.55).astype(np.uint8)
+    sizes = np.stack([rng.integers(6, h + 1, n), rng.integers(6, w + 1, n)], axis=1).astype(np.int32)
+    ex = imf.get_extractor(four_directions=True, shape=True, moments=True)
+    want = ex.extract_host_hwc(img, mask, sizes)
+    got = ex.extract_host_hwc(img, imf.pack_mask_bits(mask), sizes, masks_packed=True)
+    assert np.array_equal(got, want, equal_nan=True)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    out = torch.empty(want.shape, dtype=torch.float64).pin_memory().numpy()
+    ex.extract_host_hwc(pin(img), pin(imf.pack_mask_bits(mask)), sizes, out=out, masks_packed=True)   # direct H2D / D2H
+    assert np.array_equal(out, want, equal_nan=True)
+    # planar layout: every plane packed on its own (plane stride padded to a multiple of 8 elements)
+    stride = imf.plane_stride_for(h, w)
+    pl = np.zeros((n, c, stride), np.uint16)
+    pm = np.zeros((n, c, stride), np.uint8)
+    pl[:, :, :h * w] = _planar(img).reshape(n, c, h * w)
+    pm[:, :, :h * w] = _planar(mask).reshape(n, c, h * w)
+    want = ex.extract_host_planar(pl, pm, hs=h, ws=w)
+    got = ex.extract_host_planar(pl, imf.pack_mask_bits(pm.reshape(n * c, stride)), hs=h, ws=w, masks_packed=True)
+    assert np.array_equal(got, want, equal_nan=True)
+
+
 def test_torch_ops_direct(torch_mod):
     """torch.ops.imfeat.extract / glcm_counts called directly (context kept by the extension, current stream from
     torch) give the same bits as the FeatureExtractor route, also under CUDA-graph capture."""
