@@ -213,13 +213,17 @@ def side_records(torch, imf, dev, local, planes, masks, n_obj, steps, peak):
     n5, c5, s5 = 8192, 18, 128
     p5, m5, z5 = ex4.synth(SEED + 5, 0, n5, c5, s5, s5, with_masks=True, variable=True, hmin=16, wmin=16, mask_shrink=32)
     out5 = torch.empty((n5, ex4.row_width(c5)), dtype=torch.float64, device=dev)
+    ex4.enable_timing(True)
+    ex4.kernel_times(reset=True)
     ms5 = _timed(torch, lambda: ex4.extract_planar(p5, m5, z5, hs=s5, ws=s5, out=out5), 3, warmup=1)
+    k5, c5n = ex4.kernel_times(reset=True)
     px5 = float((z5[:, 0].double() * z5[:, 1].double()).sum().item()) * c5
     b5 = px5 * 3 + n5 * 8 * F_FULL * c5
     rec["cfg5_variable_sparse"] = {
         "workload": "configs[4]: %d objects, h,w ~ U{16..128}, 18 channels, masks 1-10%% of the tile, fixed stride 128x128 + size table, all feature blocks" % n5,
         "ms": ms5, "objects_per_s": n5 / (ms5 * 1e-3), "gpixel_per_s": px5 / (ms5 * 1e-3) / 1e9,
-        "roofline_path_frac": b5 / (ms5 * 1e-3) / 1e9 / peak}
+        "roofline_path_frac": b5 / (ms5 * 1e-3) / 1e9 / peak,
+        "kernels": [{"kernel": KERNEL_GROUPS[k], "ms_per_launch": k5[k] / c5n[k]} for k in range(4) if c5n[k]]}
     del p5, m5, z5, out5
     # ---- full 16-bit range: K12's window fails for every tile, K2 full-range + K1 FP64 + K3 general quantiser ----
     g = torch.Generator(device=dev)
@@ -227,9 +231,12 @@ def side_records(torch, imf, dev, local, planes, masks, n_obj, steps, peak):
     p16 = torch.randint(0, 65536, tuple(planes.shape), generator=g, device=dev, dtype=torch.int32).to(torch.uint16)
     out16 = torch.empty((n_obj, ex4.row_width(C)), dtype=torch.float64, device=dev)
     ms16 = _timed(torch, lambda: ex4.extract_planar(p16, masks, hs=HS, ws=WS, out=out16), 3, warmup=1)
+    k16, c16 = ex4.kernel_times(reset=True)
+    ex4.enable_timing(False)
     rec["full_16bit_range"] = {
         "workload": "same masks, pixels uniform over 0..65535: every tile leaves the 4,096-value histogram window and the integer moment range",
-        "ms": ms16, "objects_per_s": n_obj / (ms16 * 1e-3)}
+        "ms": ms16, "objects_per_s": n_obj / (ms16 * 1e-3),
+        "kernels": [{"kernel": KERNEL_GROUPS[k], "ms_per_launch": k16[k] / c16[k]} for k in range(4) if c16[k]]}
     return rec
 
 

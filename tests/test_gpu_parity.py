@@ -534,20 +534,26 @@ def test_pinned_batcher_end_to_end(torch_mod):
     """Variable-size objects through the pinned batcher == per-object oracle rows."""
     rng = np.random.default_rng(17)
     ex = imf.get_extractor()
-    b = imf.PinnedBatcher(ex, capacity=16, hs=96, ws=80, channels=3, with_masks=True)
     objs = []
     for k in range(37):
         h, w = int(rng.integers(8, 97)), int(rng.integers(8, 81))
         img = rng.integers(0, 4096, (h, w, 3)).astype(np.uint16)
         m = rng.random((h, w, 3)) < 0.6
         objs.append((img, m))
-        b.add(img, m, label=k)
-    table, labels = b.finish()
-    assert labels == list(range(37)) and table.shape == (37, 69)
     cols = imf.feature_columns(3)
+    tables = []
+    # synchronous with byte masks; double-buffered in the background with byte masks and with bit-packed masks
+    for kw in (dict(asynchronous=False), dict(), dict(packed_masks=True)):
+        b = imf.PinnedBatcher(ex, capacity=8, hs=96, ws=80, channels=3, with_masks=True, **kw)
+        for k, (img, m) in enumerate(objs):
+            b.add(img, m, label=k)
+        table, labels = b.finish()
+        assert labels == list(range(37)) and table.shape == (37, 69)
+        tables.append(table)
+    assert np.array_equal(tables[0], tables[1], equal_nan=True) and np.array_equal(tables[0], tables[2], equal_nan=True)
     for k, (img, m) in enumerate(objs):
         want = c_oracle.table(_planar(img[None]), _planar(m[None].astype(np.uint8)))
-        compare_tables(table[k:k + 1], want, cols, label="batcher %d" % k)
+        compare_tables(tables[0][k:k + 1], want, cols, label="batcher %d" % k, images=[img], masks=[m])
 
 
 def test_wide_range_tiles_through_host_pipeline(torch_mod):
