@@ -19,20 +19,22 @@
 
 namespace imfeat {
 
+constexpr int kK12Clc = 64;     // counts below this take c * log2(c) from shared memory
 struct K12Smem {
     K2cSmem h;                  // 4,096-bin histogram (16-bit counters) + percentile scratch of this warp
     K1Pending pending[32];      // finished tiles whose moment epilogues run 32 at a time
+    double clc[kK12Clc];        // c * log2(c), c < kK12Clc (0 for c = 0, 1)
 };
 
-// One pixel into the warp's histogram (fire-and-forget).  in1 = 1 when the pixel counts (inside the mask), else 0:
+// One pixel into the warp's histogram (fire-and-forget).  inb = all ones when the pixel counts (inside the mask), else 0:
 // then the increment is 0, on word `lane` (distinct banks; equal background values outside the mask would
 // otherwise serialise on one address).  Two issue slots fewer than k2c_px: the increment 1 << 16 * (bin & 1) is one
 // wrapping funnel shift (only the low five bits of the amount count), with the mask bit as its source.
 template <bool MASKED>
-__device__ __forceinline__ void k12_px(K2cSmem& S, uint32_t x, uint32_t in1, uint32_t inb, uint32_t base, uint32_t lane4) {
+__device__ __forceinline__ void k12_px(K2cSmem& S, uint32_t x, uint32_t inb, uint32_t base, uint32_t lane4) {
     const uint32_t bin = x - base;
     uint32_t off = (bin << 1) & (uint32_t)(kK2cWords * 4 - 4);
-    const uint32_t inc = __funnelshift_l(0u, MASKED ? in1 : 1u, bin << 4);
+    const uint32_t inc = __funnelshift_l(0u, MASKED ? (inb & 1u) : 1u, bin << 4);
     if (MASKED) off = (off & inb) | (lane4 & ~inb);
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_addr(S.hist) + off), "r"(inc) : "memory");
 }
@@ -70,8 +72,8 @@ __device__ __forceinline__ void k12_vec(K2cSmem& S, const uint4& v, const uint2&
         k1_px_int(y1, s2, st.S3[1], st.S4[1]);
         if (HIST) {
             const uint32_t lane4 = 4u * (threadIdx.x & 31);
-            k12_px<MASKED>(S, x0, (nz[k >> 1] >> (16 * (k & 1))) & 1u, __byte_perm(h[k], 0u, 0x1010), base, lane4);
-            k12_px<MASKED>(S, x1, (nz[k >> 1] >> (16 * (k & 1) + 8)) & 1u, __byte_perm(h[k], 0u, 0x3232), base, lane4);
+            k12_px<MASKED>(S, x0, __byte_perm(h[k], 0u, 0x1010), base, lane4);
+            k12_px<MASKED>(S, x1, __byte_perm(h[k], 0u, 0x3232), base, lane4);
         }
     }
     st.S2 += s2;
@@ -80,7 +82,7 @@ __device__ __forceinline__ void k12_vec(K2cSmem& S, const uint4& v, const uint2&
 // Percentiles (numpy "linear", bit for bit) and entropy from the warp's histogram whose bin 0 is the value
 // `base`; the values present lie in [vmin, vmax].  Clears the used range.  (K2c's second half, with the walk
 // starting at the block of the minimum instead of bin 0.)
-__device__ __forceinline__ void k12_order_entropy(K2cSmem& S, const Params& P, double* o, int n, uint32_t base,
+__device__ __forceinline__ void k12_order_entropy(K2cSmem& S, const double* clc, const Params& P, double* o, int n, uint32_t base,
                                                   uint32_t vmin, uint32_t vmax, int lane) {
     const int b_lo = (int)(vmin - base), b_hi = (int)(vmax - base);
     {
@@ -135,8 +137,13 @@ __device__ __forceinline__ void k12_order_entropy(K2cSmem& S, const Params& P, d
         const uint4 q = hist4[k];
         if ((q.x | q.y | q.z | q.w) == 0u) continue;
         hist4[k] = make_uint4(0u, 0u, 0u, 0u);
-        if (((q.x | q.y | q.z | q.w) & 0xfffefffeu) == 0u) continue;
         const uint32_t wv4[4] = {q.x, q.y, q.z, q.w};
+        // small counts (all but flat backgrounds): c * log2(c) from shared memory, no branch per count
+        if (((q.x | q.y | q.z | q.w) & ~(0x00010001u * (uint32_t)(kK12Clc - 1))) == 0u) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) hs += clc[wv4[u] & 0xffffu] + clc[wv4[u] >> 16];
+            continue;
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const uint32_t c0 = wv4[u] & 0xffffu, c1 = wv4[u] >> 16;
@@ -159,6 +166,7 @@ __global__ void __launch_bounds__(32, 20) k12_basic_kernel(const __grid_constant
     K1Pending* pending = SS.pending;
     const int lane = threadIdx.x;
     for (int k = lane; k < kK2cWords; k += 32) S.hist[k] = 0u;
+    for (int k = lane; k < kK12Clc; k += 32) SS.clc[k] = (double)k * __ldg(P.log2tab + k);      // log2tab[0] = 0
     __syncwarp();
     int n_pending = 0;
     long long tnext = next_tile(P.sched + 0);
@@ -262,7 +270,7 @@ __global__ void __launch_bounds__(32, 20) k12_basic_kernel(const __grid_constant
                     if (MASKED) m = __ldg(mk2 + idx);
                     k12_vec<MASKED, true>(S, v, m, pi, base, st);
                 }
-                if (tail_ok) k12_px<false>(S, xt, 1u, 0xffffffffu, base, 0u);
+                if (tail_ok) k12_px<false>(S, xt, 0xffffffffu, base, 0u);
             } else {
                 for (; idx + 32 * (kU - 1) < nfull; idx += 32 * kU) {
                     uint4 v[kU];
@@ -309,7 +317,7 @@ __global__ void __launch_bounds__(32, 20) k12_basic_kernel(const __grid_constant
             __syncwarp();                                  // the histogram adds of all lanes are done
             if (hist_on) {
                 if (n_eff != 0u && vmin >= base && vmax < base + (uint32_t)kK2cBins) {
-                    k12_order_entropy(S, P, o, (int)n_eff, base, vmin, vmax, lane);
+                    k12_order_entropy(S, SS.clc, P, o, (int)n_eff, base, vmin, vmax, lane);
                     order_done = true;
                 } else if (n_eff != 0u) {
                     // the window did not hold: the counts are meaningless (offsets wrapped around) -- wipe them
