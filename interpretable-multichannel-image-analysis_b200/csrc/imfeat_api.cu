@@ -554,7 +554,7 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
             else ring::k3_glcm_kernel<false, false, 2><<<g3, ring::kK3Threads, smem3, st>>>(P, maxpx, pf);
             ctx->launches += 1;
         } else {
-            int rc3 = launch_k3<false>(ctx, masked, st, P, maxpx);
+            int rc3 = launch_k3<false>(ctx, masked, st, P, k3_q8_capacity(P.hs, P.ws, masked));
             if (rc3) return rc3;
         }
         IMFEAT_MARK(2)
@@ -670,8 +670,8 @@ int imfeat_glcm_counts_device(imfeat_ctx* ctx, const uint16_t* d_planes, const u
     fill_params(P, ctx, d_planes, d_masks, d_sizes, nullptr, nullptr, n_objects, c, c, hs, ws,
                 plane_stride, &o, scratch, width, nullptr);
     P.counts = d_counts;
-    const int maxpx = ((P.hs * P.ws + 7) & ~7);
     const bool masked = d_masks != nullptr;
+    const int maxpx = k3_q8_capacity(P.hs, P.ws, masked);
     // the tile counter of K3's dynamic scheduler (slot 2 of a work-counter set)
     P.sched = ctx->d_sched + 8 * (ctx->sched_head++ % kSchedSlots);
     CU(cudaMemsetAsync(P.sched, 0, sizeof(unsigned int) * 8, st));

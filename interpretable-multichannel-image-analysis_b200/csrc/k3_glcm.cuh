@@ -119,19 +119,32 @@ __device__ __forceinline__ uint32_t k3_bits(const uint32_t* b, int off) {
     return __funnelshift_r(b[w], b[w + 1], off & 31);
 }
 
+// Row pitch (bytes) of the quantised tile in shared memory.  Masked tiles whose rows are a multiple of 8 pixels get
+// an ODD number of words per row, and the lanes of a warp take items of consecutive ROWS (same column block): the
+// 32 word loads of a warp then hit 32 different banks.  With the compact pitch of a 64-pixel row (16 words) and
+// row-major items, rows two apart fell on the same banks: 3.4 wavefronts per load instead of 1 (ncu, source page),
+// a third of all shared-memory traffic of the front kernel and more than half of the bins kernel's loads.
+template <bool MASKED>
+__host__ __device__ __forceinline__ int k3_pitch(int w) {
+    return (MASKED && w >= 32 && (w & 7) == 0) ? (((w >> 2) | 1) << 2) : w;
+}
+// bytes of quantised pixels a batch of stride hs x ws can need (pitch <= w + 4)
+__host__ __device__ inline int k3_q8_capacity(int hs, int ws, bool masked) { return ((masked ? hs * (ws + 4) : hs * ws) + 7) & ~7; }
+
 // Pairs (r, c) -> (r + dr, c + dc) with both pixels inside the box rows [br0, br1], columns
 // [bc0, bc1] (the whole tile, or the bounding box of the mask: pairs outside it cannot exist).
 template <bool MASKED, int NG>
 __device__ __forceinline__ K3Geom k3_geom(int w, int dr, int dc, int br0, int br1, int bc0, int bc1) {
     K3Geom G;
+    const int pitch = k3_pitch<MASKED>(w);
     G.r0 = br0;
     G.nrows = br1 - dr - br0 + 1;                  // dr >= 0 for all supported directions
     G.c0 = bc0 + (dc < 0 ? -dc : 0);
     G.c1 = bc1 + 1 - (dc > 0 ? dc : 0);
-    G.w = w;
-    G.doff = dr * w + dc;
+    G.w = pitch;                                   // quantised pixels: row pitch and pair offset in bytes
+    G.doff = dr * pitch + dc;
     G.aligned = 0; G.base_j = dc < 0; G.ws = 0; G.sb = 0;
-    G.pad[0] = G.pad[1] = G.pad[2] = 0;
+    G.pad[0] = 0; G.pad[1] = w; G.pad[2] = dr * w + dc;      // mask bits stay compact: their row pitch and pair offset
     if (G.nrows <= 0 || G.c1 <= G.c0) { G.items = 0; G.ipr = 1; G.rcp = 1.0f; G.nrows = 0; return G; }
     // unmasked tiles only: the aligned side starts at column bc0 = 0.  (Widening a mask's bounding box to the
     // left to get there was measured slower: up to a third more items.)
@@ -142,7 +155,7 @@ __device__ __forceinline__ K3Geom k3_geom(int w, int dr, int dc, int br0, int br
         G.sb = (other & 3) << 3;
     }
     G.ipr = (G.c1 - G.c0 + 4 * NG - 1) / (4 * NG); // items per row
-    G.rcp = __frcp_rn((float)G.ipr);
+    G.rcp = __frcp_rn((float)(MASKED ? G.nrows : G.ipr));     // masked: items run down the rows first (see k3_pitch)
     G.items = G.nrows * G.ipr;
     return G;
 }
@@ -161,8 +174,15 @@ template <bool MASKED, int NG>
 __device__ __forceinline__ bool k3_item(const K3Group& Gp, const K3Geom& G, int item, uint32_t (&I4)[NG],
                                         uint32_t (&J4)[NG], uint32_t& pm) {
     constexpr int NP = 4 * NG;
-    const int r = (int)(((float)item + 0.5f) * G.rcp);
-    const int c = G.c0 + NP * (item - r * G.ipr);
+    int r, c;
+    if (MASKED) {                                  // column-major: consecutive items = consecutive rows
+        const int k = (int)(((float)item + 0.5f) * G.rcp);
+        r = item - k * G.nrows;
+        c = G.c0 + NP * k;
+    } else {
+        r = (int)(((float)item + 0.5f) * G.rcp);
+        c = G.c0 + NP * (item - r * G.ipr);
+    }
     const int nv = min(NP, G.c1 - c);
     const int oi = (G.r0 + r) * G.w + c, oj = oi + G.doff;
     pm = ((1u << NP) - 1u) >> (NP - nv);
@@ -183,7 +203,8 @@ __device__ __forceinline__ bool k3_item(const K3Group& Gp, const K3Geom& G, int 
         return true;
     }
     if (MASKED) {
-        pm &= k3_bits(Gp.mbits, oi) & k3_bits(Gp.mbits, oj);
+        const int mi = (G.r0 + r) * G.pad[1] + c;
+        pm &= k3_bits(Gp.mbits, mi) & k3_bits(Gp.mbits, mi + G.pad[2]);
         if (pm == 0u) return false;
     }
     const uint32_t* bi = Gp.q8 + (oi >> 2);
@@ -490,6 +511,8 @@ k3a_front_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t tile
                 }
             }
         };
+        const int pitch = k3_pitch<MASKED>(tw), cpr = tw >> 3;         // padded pitch: 8-pixel chunks per row
+        const float rcpr = __frcp_rn((float)max(cpr, 1));
         auto quant_chunk = [&](int idx, const uint4& v) {              // out-of-mask pixels may exceed the maximum:
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};               // their bytes are never part of a pair
             uint32_t q[4];
@@ -502,7 +525,14 @@ k3a_front_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t tile
                 for (int k = 0; k < 4; ++k)
                     q[k] = __byte_perm(k3_quant(w4[k] & 0xffffu, mul, sh), k3_quant(w4[k] >> 16, mul, sh), 0x0040);
             }
-            *reinterpret_cast<uint2*>(Gp.q8 + 2 * idx) = make_uint2(__byte_perm(q[0], q[1], 0x5410), __byte_perm(q[2], q[3], 0x5410));
+            const uint32_t lo = __byte_perm(q[0], q[1], 0x5410), hi = __byte_perm(q[2], q[3], 0x5410);
+            if (pitch == tw) {
+                *reinterpret_cast<uint2*>(Gp.q8 + 2 * idx) = make_uint2(lo, hi);
+            } else {                                       // the chunk lies inside one row (tw % 8 == 0)
+                const int ra = (int)(((float)idx + 0.5f) * rcpr);
+                uint32_t* dst = Gp.q8 + ((ra * pitch) >> 2) + 2 * (idx - ra * cpr);
+                dst[0] = lo; dst[1] = hi;
+            }
         };
         {
             constexpr int kU = 4;                          // loads in flight per lane
