@@ -60,6 +60,13 @@ struct imfeat_ctx {
     int timing;
     int t_head, t_pending;
     cudaEvent_t t_ev[kTimingSlots][5];
+    cudaEvent_t t_side[kTimingSlots][2];   // K4 on the side stream (overlap mode): its own start / end
+    // overlap mode: K4w runs on a side stream next to K3 (its few resident warps fill the issue slots the
+    // shared-memory-bound GLCM kernels leave free)
+    int env_overlap, env_k4_fill;
+    cudaStream_t side[4];
+    cudaEvent_t fork_ev[8], join_ev[8];
+    unsigned int side_head;
     unsigned t_mask[kTimingSlots];
     double t_ms[4];
     long long t_calls[4];
@@ -158,6 +165,9 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
         ctx->env_fuse12 = flag("IMFEAT_FUSE12", 1);          // 1: the basic block in one pass (k12_basic.cuh); 0: K1 then K2c
         ctx->env_k3_table = flag("IMFEAT_K3_TABLE", 0);      // 32 / 64: force the table size of the bins kernel (0: by mask)
         ctx->env_k3_ring = flag("IMFEAT_K3_RING", 1);       // 1: unmasked tiles through the one-kernel ring variant (k3_ring.cuh)
+        ctx->env_overlap = flag("IMFEAT_OVERLAP", 0);       // 1: K4w on a side stream next to K3, 2: next to K12 as well (measured: no gain); 0: one stream
+        ctx->env_k4_fill = flag("IMFEAT_K4_FILL", 4);       // resident K4w warps per SM while it runs next to K3
+        if (ctx->env_k4_fill < 1) ctx->env_k4_fill = 1;
     }
     ctx->sm_count = prop.multiProcessorCount;
     // log2 table, computed on the host in double precision (k = 0 maps to 0, never used)
@@ -213,8 +223,8 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2c_bps[1], k2c_order_entropy_kernel<true>, kK2cThreads, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k12_bps[0], k12_basic_kernel<false>, 32, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k12_bps[1], k12_basic_kernel<true>, 32, 0);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4w_bps[0], k4w_shape_kernel<false>, 32, 0);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4w_bps[1], k4w_shape_kernel<true>, 32, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4w_bps[0], k4w_shape_kernel<false, true>, 32, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4w_bps[1], k4w_shape_kernel<true, true>, 32, 0);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4_bps[0], k4_shape_kernel<false>, kK4Threads, sizeof(K4Smem));
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k4_bps[1], k4_shape_kernel<true>, kK4Threads, sizeof(K4Smem));
     if (e != cudaSuccess) {
@@ -247,9 +257,17 @@ int imfeat_destroy(imfeat_ctx* ctx) {
         if (ctx->streams[b]) cudaStreamDestroy(ctx->streams[b]);
         if (ctx->done[b]) cudaEventDestroy(ctx->done[b]);
     }
-    for (int sl = 0; sl < kTimingSlots; ++sl)
+    for (int sl = 0; sl < kTimingSlots; ++sl) {
         for (int k = 0; k < 5; ++k)
             if (ctx->t_ev[sl][k]) cudaEventDestroy(ctx->t_ev[sl][k]);
+        for (int k = 0; k < 2; ++k)
+            if (ctx->t_side[sl][k]) cudaEventDestroy(ctx->t_side[sl][k]);
+    }
+    for (int k = 0; k < 4; ++k) if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
+    for (int k = 0; k < 8; ++k) {
+        if (ctx->fork_ev[k]) cudaEventDestroy(ctx->fork_ev[k]);
+        if (ctx->join_ev[k]) cudaEventDestroy(ctx->join_ev[k]);
+    }
     if (ctx->d_log2tab) cudaFree(ctx->d_log2tab);
     if (ctx->d_gfix) cudaFree(ctx->d_gfix);
     if (ctx->d_worklist) cudaFree(ctx->d_worklist);
@@ -427,6 +445,13 @@ static int timing_resolve(imfeat_ctx* ctx, int slot) {
         ctx->t_calls[k] += 1;
         prev = k;
     }
+    if (m & 16u) {                                         // K4 ran on the side stream, timed by its own events
+        float ms = 0.f;
+        CU(cudaEventSynchronize(ctx->t_side[slot][1]));
+        CU(cudaEventElapsedTime(&ms, ctx->t_side[slot][0], ctx->t_side[slot][1]));
+        ctx->t_ms[3] += ms;
+        ctx->t_calls[3] += 1;
+    }
     ctx->t_mask[slot] = 0;
     return IMFEAT_OK;
 }
@@ -456,6 +481,54 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
     }
     const bool masked = P.masks != nullptr;
     const long long sm = ctx->sm_count;
+    int joined = -1;                                       // overlap mode: index of the join event the call ends with
+    auto launch_k4w = [&](cudaStream_t s4, long long warps_per_sm) {
+        const long long resw = sm * warps_per_sm;
+        const int gw = (int)(P.n_tiles < resw ? P.n_tiles : resw);
+        const int cpr = P.ws >> 3;
+        const bool general = P.sizes != nullptr || (P.ws & 7) != 0 || (cpr & (cpr - 1)) != 0 || cpr > 32;
+        if (general) {
+            if (masked) k4w_shape_kernel<true, true><<<gw, 32, 0, s4>>>(P);
+            else k4w_shape_kernel<false, true><<<gw, 32, 0, s4>>>(P);
+        } else {
+            if (masked) k4w_shape_kernel<true, false><<<gw, 32, 0, s4>>>(P);
+            else k4w_shape_kernel<false, false><<<gw, 32, 0, s4>>>(P);
+        }
+        ctx->launches += 1;
+    };
+    const bool k4_warp_tiles = P.hs <= kK4FastDim && P.ws <= kK4FastDim && P.hs * P.ws <= kK4FastPixels && ctx->env_k4_warp != 0;
+    const bool k4_overlap = (o->want_shape || o->want_moments) && o->want_glcm && k4_warp_tiles && ctx->env_overlap != 0;
+    auto fork_k4 = [&]() -> int {
+        // K4w next to the kernels that follow on `st`: a few resident warps per SM on a side stream.  They fill the
+        // issue slots the shared-memory-bound GLCM kernels leave free; when they are done their registers go to the
+        // CTAs of those kernels that were still waiting for room.
+        const unsigned k = ctx->side_head++;
+        cudaStream_t s4 = ctx->side[k & 3u];
+        if (!s4) { CU(cudaStreamCreateWithFlags(&ctx->side[k & 3u], cudaStreamNonBlocking)); s4 = ctx->side[k & 3u]; }
+        cudaEvent_t& fe = ctx->fork_ev[k & 7u];
+        cudaEvent_t& je = ctx->join_ev[k & 7u];
+        if (!fe) CU(cudaEventCreateWithFlags(&fe, cudaEventDisableTiming));
+        if (!je) CU(cudaEventCreateWithFlags(&je, cudaEventDisableTiming));
+        CU(cudaEventRecord(fe, st));
+        CU(cudaStreamWaitEvent(s4, fe, 0));
+        if (slot >= 0) {
+            for (int q = 0; q < 2; ++q)
+                if (!ctx->t_side[slot][q]) CU(cudaEventCreate(&ctx->t_side[slot][q]));
+            CU(cudaEventRecord(ctx->t_side[slot][0], s4));
+        }
+        launch_k4w(s4, ctx->env_k4_fill);
+        if (slot >= 0) {
+            CU(cudaEventRecord(ctx->t_side[slot][1], s4));
+            ctx->t_mask[slot] |= 16u;
+        }
+        CU(cudaEventRecord(je, s4));
+        joined = (int)(k & 7u);
+        return IMFEAT_OK;
+    };
+    if (k4_overlap && ctx->env_overlap == 2) {             // from the start: next to K12 as well
+        int rcf = fork_k4();
+        if (rcf) return rcf;
+    }
     if (o->want_basic) {
         const int g2 = (int)(P.n_tiles < sm ? P.n_tiles : sm);
         const int ng2 = k2_groups(ctx);
@@ -524,15 +597,16 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
     // K4 goes before K3: with several GPUs the all-gather of the previous batch then overlaps the
     // dynamically scheduled warp-per-tile kernels (K1, K2c, K4w) and is over when K3 starts, whose
     // persistent one-CTA-per-SM grid would otherwise wait for the SMs the collective holds
-    if (o->want_shape || o->want_moments) {
-        const bool warp_tiles = P.hs <= kK4FastDim && P.ws <= kK4FastDim && P.hs * P.ws <= kK4FastPixels &&
-                                ctx->env_k4_warp != 0;
-        if (warp_tiles) {
+    if (k4_overlap && joined < 0) {
+        // the side stream's work is queued here, behind K12 (IMFEAT_OVERLAP=1), so that it is the first to take
+        // its few warp slots when K12 has drained; the GLCM kernels are queued after it on `st`
+        int rcf = fork_k4();
+        if (rcf) return rcf;
+    } else if (!k4_overlap && (o->want_shape || o->want_moments)) {
+        if (k4_warp_tiles) {
             // every tile of this batch fits the fast path: one warp per tile, many warps per SM
-            const long long resw = sm * (ctx->k4w_bps[masked] > 0 ? ctx->k4w_bps[masked] : 1);
-            const int gw = (int)(P.n_tiles < resw ? P.n_tiles : resw);
-            if (masked) k4w_shape_kernel<true><<<gw, 32, 0, st>>>(P);
-            else k4w_shape_kernel<false><<<gw, 32, 0, st>>>(P);
+            launch_k4w(st, ctx->k4w_bps[masked] > 0 ? ctx->k4w_bps[masked] : 1);
+            ctx->launches -= 1;                            // counted below
         } else {
             const long long res4 = sm * (ctx->k4_bps[masked] > 0 ? ctx->k4_bps[masked] : 1);
             const int g4 = (int)(P.n_tiles < res4 ? P.n_tiles : res4);
@@ -559,6 +633,7 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
         }
         IMFEAT_MARK(2)
     }
+    if (joined >= 0) CU(cudaStreamWaitEvent(st, ctx->join_ev[joined], 0));
 #undef IMFEAT_MARK
     CU(cudaGetLastError());
     return IMFEAT_OK;

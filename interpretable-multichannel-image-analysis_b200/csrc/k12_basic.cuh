@@ -157,8 +157,11 @@ __device__ __forceinline__ void k12_order_entropy(K2cSmem& S, const double* clc,
     __syncwarp();
 }
 
+#ifndef IMFEAT_K12_WARPS
+#define IMFEAT_K12_WARPS 20            // resident warps per SM the register budget is set for
+#endif
 template <bool MASKED>
-__global__ void __launch_bounds__(32, 20) k12_basic_kernel(const __grid_constant__ Params P,
+__global__ void __launch_bounds__(32, IMFEAT_K12_WARPS) k12_basic_kernel(const __grid_constant__ Params P,
                                                            uint32_t* __restrict__ worklist,
                                                            uint32_t* __restrict__ worklist_count) {
     __shared__ K12Smem SS;

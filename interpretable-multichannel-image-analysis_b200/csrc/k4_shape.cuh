@@ -383,8 +383,13 @@ struct K4Pending {
     unsigned long long mq[10];
 };
 
-template <bool MASKED>
-__global__ void __launch_bounds__(32, 20) k4w_shape_kernel(const __grid_constant__ Params P) {
+#ifndef IMFEAT_K4W_WARPS
+#define IMFEAT_K4W_WARPS 20            // resident warps per SM the register budget is set for
+#endif
+// GENERAL: the batch has tiles whose rows are not 8, 16, .. 256 pixels long (a size table, or such a stride); the
+// kernel then carries the general vector pass as well, which costs the other variant registers (and 4 % of its speed).
+template <bool MASKED, bool GENERAL>
+__global__ void __launch_bounds__(32, IMFEAT_K4W_WARPS) k4w_shape_kernel(const __grid_constant__ Params P) {
     __shared__ uint32_t mrow[kK4wWords];
     __shared__ uint32_t brow[kK4wWords];
     __shared__ K4Pending pending[kK4wBatch];
@@ -491,6 +496,83 @@ __global__ void __launch_bounds__(32, 20) k4w_shape_kernel(const __grid_constant
                 mq[5] = C2 * B00 + 2ull * C1 * B01 + B02; mq[8] = C2 * B10 + 2ull * C1 * B11 + B12;
                 mq[9] = C3 * B00 + 3ull * C2 * B01 + 3ull * C1 * B02 + B03;
             }
+        } else if (GENERAL && w >= 8) {
+            // General vector pass (any w >= 8): 8-pixel chunks of the compact plane, lane-strided, the same 128-bit
+            // pixel / 64-bit mask loads.  A chunk starts at (r, c) = divmod(8 * idx, w) and may run over the end of
+            // its row (once: w >= 8): it is then worked off as two segments, (r, c) with its first w - c pixels and
+            // (r + 1, c - w) with the others -- the column of pixel k is c + k in both, with a negative c in the
+            // second.  The column is folded into the local sums per segment (it changes from chunk to chunk), all
+            // in wrapping integer arithmetic whose true values are non-negative and fit.
+            for (int k = lane; k < h * Pw; k += 32) mrow[k] = 0u;
+            __syncwarp();
+            const int n = T.n, nchunk = (n + 7) >> 3;
+            const float rtw = __frcp_rn((float)w);
+            const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
+            const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
+            auto seg = [&](int r, int c, uint4 v, uint32_t n0, uint32_t n1) {      // n0 / n1: 0xff per pixel of the segment
+                const uint32_t b03 = n0 & 0x01010101u, b47 = n1 & 0x01010101u;
+                const uint32_t bits8 = (((b03 * 0x01020408u) >> 24) & 0xfu) | (((b47 * 0x01020408u) >> 20) & 0xf0u);
+                if (bits8 == 0u) return;
+                {
+                    const uint32_t bb = c < 0 ? bits8 >> (-c) : bits8;
+                    const int pos = max(c, 0), sh = pos & 31;
+                    uint32_t* wp = mrow + r * Pw + (pos >> 5);
+                    atomicOr(wp, bb << sh);
+                    if (sh > 24 && (bb >> (32 - sh)) != 0u) atomicOr(wp + 1, bb >> (32 - sh));
+                }
+                const uint32_t cnt = __popc(bits8);
+                const uint32_t sk = __dp4a(b47, 0x07060504u, __dp4a(b03, 0x03020100u, 0u));
+                const uint32_t sk2 = __dp4a(b47, 0x31241910u, __dp4a(b03, 0x09040100u, 0u));
+                const uint32_t r1 = (uint32_t)r, r2 = r1 * r1, cu = (uint32_t)c;
+                const uint32_t colsum = cu * cnt + sk;
+                area += cnt; sr += r1 * cnt; srr += r2 * cnt;
+                sc += colsum; src += r1 * colsum; scc += cu * cu * cnt + 2u * cu * sk + sk2;
+                rmin = min(rmin, r); rmax = max(rmax, r);
+                cmin = min(cmin, c + __ffs(bits8) - 1); cmax = max(cmax, c + 31 - __clz(bits8));
+                if (want_mom) {
+                    v.x &= __byte_perm(n0, 0u, 0x1100); v.y &= __byte_perm(n0, 0u, 0x3322);
+                    v.z &= __byte_perm(n1, 0u, 0x1100); v.w &= __byte_perm(n1, 0u, 0x3322);
+                    const uint32_t s0 = __dp2a_lo(v.w, 0x0101u, __dp2a_lo(v.z, 0x0101u, __dp2a_lo(v.y, 0x0101u, __dp2a_lo(v.x, 0x0101u, 0u))));
+                    const uint32_t s1 = __dp2a_lo(v.w, 0x0706u, __dp2a_lo(v.z, 0x0504u, __dp2a_lo(v.y, 0x0302u, __dp2a_lo(v.x, 0x0100u, 0u))));
+                    const uint32_t s2 = __dp2a_lo(v.w, 0x3124u, __dp2a_lo(v.z, 0x1910u, __dp2a_lo(v.y, 0x0904u, __dp2a_lo(v.x, 0x0100u, 0u))));
+                    const uint32_t s3 = __dp2a_lo(v.w, 0x5800u, __dp2a_lo(v.w, 0xffd8u, __dp2a_lo(v.z, 0x7d40u, __dp2a_lo(v.y, 0x1b08u, __dp2a_lo(v.x, 0x0100u, 0u)))));
+                    // sum_k I_k (c + k)^q, q = 0..3 (64-bit wrapping; the true values are >= 0)
+                    const unsigned long long C1 = (unsigned long long)(long long)c, C2 = C1 * C1;
+                    const unsigned long long t0 = s0, t1 = C1 * s0 + s1, t2 = C2 * s0 + 2ull * C1 * s1 + s2;
+                    const unsigned long long t3 = C2 * C1 * s0 + 3ull * C2 * s1 + 3ull * C1 * s2 + s3;
+                    const unsigned long long R1 = r1, R2 = r2, R3 = (unsigned long long)r2 * r1;
+                    mq[0] += t0; mq[1] += t0 * R1; mq[3] += t0 * R2; mq[6] += t0 * R3;
+                    mq[2] += t1; mq[4] += t1 * R1; mq[7] += t1 * R2;
+                    mq[5] += t2; mq[8] += t2 * R1;
+                    mq[9] += t3;
+                }
+            };
+            auto chunk = [&](int idx, const uint4& v, const uint2& m) {
+                const int p0 = idx << 3;
+                const int r = (int)(((float)p0 + 0.5f) * rtw), c = p0 - r * w;          // exact: p0 < 2^20
+                const int nv = min(8, n - p0), na = min(nv, w - c);                    // pixels of the chunk; of them in row r
+                // 0xff per pixel k < na (A) and na <= k < nv (B)
+                const unsigned long long all = nv >= 8 ? ~0ull : ((1ull << (8 * nv)) - 1ull);
+                const unsigned long long ma = na >= 8 ? ~0ull : ((1ull << (8 * na)) - 1ull);
+                uint32_t n0 = 0xffffffffu, n1 = 0xffffffffu;
+                if (MASKED) { n0 = __vcmpne4(m.x, 0u); n1 = __vcmpne4(m.y, 0u); }
+                seg(r, c, v, n0 & (uint32_t)ma, n1 & (uint32_t)(ma >> 32));
+                if (na < nv) seg(r + 1, c - w, v, n0 & (uint32_t)(all & ~ma), n1 & (uint32_t)((all & ~ma) >> 32));
+            };
+            int idx = lane;
+            for (; idx + 96 < nchunk; idx += 128) {                               // four chunks of loads in flight
+                uint4 v[4];
+                uint2 m[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    v[u] = want_mom ? ld_stream(px4 + idx + 32 * u) : make_uint4(0u, 0u, 0u, 0u);
+                    m[u] = MASKED ? __ldg(mk2 + idx + 32 * u) : make_uint2(0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) chunk(idx + 32 * u, v[u], m[u]);
+            }
+            for (; idx < nchunk; idx += 32)
+                chunk(idx, want_mom ? ld_stream(px4 + idx) : make_uint4(0u, 0u, 0u, 0u), MASKED ? __ldg(mk2 + idx) : make_uint2(0u, 0u));
         } else {
             // ---- pass A: lanes over columns, rows in sequence (four rows of loads in flight) ----
             for (int c0 = 0; c0 < w; c0 += 32) {
