@@ -326,11 +326,12 @@ static int launch_k3_nt(imfeat_ctx* ctx, bool masked, cudaStream_t st, const Par
     CU(cudaStreamIsCapturing(st, &cap));
     auto& slot = ctx->scr[ctx->scr_head++ & 1u];
     if (cap == cudaStreamCaptureStatusNone && slot.recorded) CU(cudaStreamWaitEvent(st, slot.ev, 0));
-    if (slot.bytes < (size_t)per * rec) {
+    const size_t scr_bytes = (size_t)per * (rec + sizeof(uint32_t));       // the records, then the table of their lengths
+    if (slot.bytes < scr_bytes) {
         if (cap == cudaStreamCaptureStatusNone && slot.recorded) CU(cudaEventSynchronize(slot.ev));
-        int rc = grow_buffer(ctx, st, (void**)&slot.ptr, (size_t)per * rec, "K3 scratch");
+        int rc = grow_buffer(ctx, st, (void**)&slot.ptr, scr_bytes, "K3 scratch");
         if (rc) { slot.bytes = 0; return rc; }
-        slot.bytes = (size_t)per * rec;
+        slot.bytes = scr_bytes;
     }
     for (long long c = 0; c < n_chunks; ++c) {
         const long long t0 = c * per;

@@ -3,15 +3,19 @@
 // Replaces, per channel:  np.percentile(X, 0.1 .. 0.9)  NB:242-250   shannon_entropy(X)  NB:262
 //
 // Both need the multiplicity of every raw 16-bit value of the tile.  The CTA owns one privatised
-// 65,536-bin histogram in shared memory (16-bit counters, two per word, 128 KB) plus a 1,024-bit
-// "occupied 64-value block" bitmap.  Two 512-thread groups work on two tiles at a time and take
-// turns on the table (common.cuh, "ping-pong").
+// 65,536-bin histogram in shared memory (16-bit counters, two per word, 128 KB); every thread group
+// keeps, next to it, the 256 counts of its tile's values by high byte.  The groups work on different
+// tiles and take turns on the table (common.cuh, token ring).
 //   entropy      sum_values c*log2(c) telescopes over the atomics' return values:
 //                sum_pixels G[old_p],  G[k] = (k+1)log2(k+1) - k*log2(k)   -> no read-back pass.
 //                G is held in 2^-42 fixed point and summed in 64-bit integers, so the result
 //                does not depend on the order in which the atomics resolve (bit-reproducible)
-//   percentiles  one warp walks only the occupied blocks from the bottom until the needed ranks
-//                are covered, then applies numpy's linear-interpolation formula bit for bit
+//   percentiles  two levels: one warp scans the 256 high-byte counts (one pass: which 256-value
+//                slice holds which rank, and how many pixels lie below it), then reads only the slices
+//                that hold a rank -- 1 KB of the table each, whatever the tile's value range -- and
+//                applies numpy's linear-interpolation formula bit for bit.  (Round 1 walked the occupied
+//                64-value blocks from the bottom: 30 dependent steps per tile on full-range data, 920 for
+//                a median.)
 //   clear        by re-walking the pixels (registers), never densely
 #pragma once
 #include "common.cuh"
@@ -20,8 +24,8 @@ namespace imfeat {
 
 constexpr int kK2Vec = 2;      // 16-byte vectors per thread kept in registers (pixels + returned counts)
 
-struct K2Group {
-    uint32_t coarse[32];     // bit b of word s: some pixel has a value in [64*(32*s+b), +64)
+struct alignas(16) K2Group {
+    uint32_t c256[256];      // pixels of the group's tile by value >> 8 (fire-and-forget atomics next to the table's)
     int vals[18];
     uint32_t cnt;            // masked pixel count (integer atomics)
     int constant;
@@ -46,30 +50,11 @@ __device__ __forceinline__ uint32_t k2_add(K2Smem& S, uint32_t x) {
     return (old >> sh) & 0xffffu;
 }
 
-// Occupied-block bitmap, built before the table is acquired.  A superset is enough (an empty
-// marked block only costs the percentile walk one cheap step), so each warp marks the whole block
-// range [min >> 6, max >> 6] of its pixels: packed 16-bit min/max per lane, two REDUX per warp, and
-// lane 0 publishes the range -- instead of one shared-memory atomic per pixel.
-template <bool MASKED>
-__device__ __forceinline__ void k2_range(const uint4& v, const uint2& m, uint32_t& mn2, uint32_t& mx2) {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    if (MASKED) {
-        uint32_t h[4];
-        mask_halfwords(m.x, h[0], h[1]);
-        mask_halfwords(m.y, h[2], h[3]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { mn2 = __vminu2(mn2, w[k] | ~h[k]); mx2 = __vmaxu2(mx2, w[k] & h[k]); }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { mn2 = __vminu2(mn2, w[k]); mx2 = __vmaxu2(mx2, w[k]); }
-    }
-}
-
 // PHASE 0: histogram build + entropy terms, 2: sparse clear.
 // olds (optional): the returned counts of the 8 pixels, packed 2 x 16 bit per word; when given,
 // the entropy-table look-ups are left to the caller (after the table has been handed over).
 template <int PHASE, bool MASKED>
-__device__ __forceinline__ void k2_vec(K2Smem& S, const Params& P, const uint4& v, const uint2& m,
+__device__ __forceinline__ void k2_vec(K2Smem& S, uint32_t* c256, const Params& P, const uint4& v, const uint2& m,
                                        uint32_t& cnt, uint32_t& maxold, unsigned long long& acc,
                                        uint32_t* olds = nullptr) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -83,6 +68,7 @@ __device__ __forceinline__ void k2_vec(K2Smem& S, const Params& P, const uint4& 
             if (!MASKED) {
                 if (PHASE == 0) {
                     const uint32_t old = k2_add(S, x);
+                    atomicAdd(c256 + (x >> 8), 1u);
                     if (olds) {
                         olds[k] |= old << (16 * hlf);
                     } else {
@@ -101,6 +87,7 @@ __device__ __forceinline__ void k2_vec(K2Smem& S, const Params& P, const uint4& 
                 if (PHASE == 0) {
                     const uint32_t sh = in ? ((x & 1u) << 4) : 0u;
                     uint32_t old = (atomicAdd(word, 1u << sh) >> sh) & 0xffffu;
+                    atomicAdd(c256 + (x >> 8), in ? 1u : 0u);
                     old = in ? old : 0u;
                     cnt += in ? 1u : 0u;
                     if (olds) {
@@ -118,7 +105,7 @@ __device__ __forceinline__ void k2_vec(K2Smem& S, const Params& P, const uint4& 
 }
 
 template <int PHASE, bool MASKED>
-__device__ __forceinline__ void k2_walk(K2Smem& S, const Params& P, const Tile& T, int gt, int gthreads,
+__device__ __forceinline__ void k2_walk(K2Smem& S, uint32_t* c256, const Params& P, const Tile& T, int gt, int gthreads,
                                         const uint4* vreg, const uint2* mreg, uint32_t& cnt,
                                         uint32_t& maxold, unsigned long long& acc, uint32_t (*olds)[4] = nullptr) {
     const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
@@ -127,12 +114,12 @@ __device__ __forceinline__ void k2_walk(K2Smem& S, const Params& P, const Tile& 
 #pragma unroll
     for (int i = 0; i < kK2Vec; ++i)
         if (gt + i * gthreads < nfull)
-            k2_vec<PHASE, MASKED>(S, P, vreg[i], mreg[i], cnt, maxold, acc, (PHASE == 0 && olds) ? olds[i] : nullptr);
+            k2_vec<PHASE, MASKED>(S, c256, P, vreg[i], mreg[i], cnt, maxold, acc, (PHASE == 0 && olds) ? olds[i] : nullptr);
     for (int idx = gt + kK2Vec * gthreads; idx < nfull; idx += gthreads) {
         const uint4 v = ld_reuse(px4 + idx);
         uint2 m = make_uint2(0u, 0u);
         if (MASKED) m = __ldg(mk2 + idx);
-        k2_vec<PHASE, MASKED>(S, P, v, m, cnt, maxold, acc);
+        k2_vec<PHASE, MASKED>(S, c256, P, v, m, cnt, maxold, acc);
     }
     if (gt < rem) {
         const int i = nfull * 8 + gt;
@@ -140,6 +127,7 @@ __device__ __forceinline__ void k2_walk(K2Smem& S, const Params& P, const Tile& 
             const uint32_t x = T.px[i];
             if (PHASE == 0) {
                 const uint32_t old = k2_add(S, x);
+                atomicAdd(c256 + (x >> 8), 1u);
                 acc += k2_gfix(S, P, old);
                 maxold = max(maxold, old);
                 if (MASKED) ++cnt;
@@ -150,100 +138,75 @@ __device__ __forceinline__ void k2_walk(K2Smem& S, const Params& P, const Tile& 
     }
 }
 
-template <bool MASKED>
-__device__ __forceinline__ void k2_mark_walk(uint32_t* coarse, const Tile& T, int gt, int gthreads,
-                                             const uint4* vreg, const uint2* mreg) {
-    const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
-    const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
-    const int nfull = T.n >> 3, rem = T.n & 7;
-    uint32_t mn2 = 0xffffffffu, mx2 = 0u;
-    bool any = !MASKED;
+// numpy percentile (method "linear") from the histogram; ranks are 0-based positions in the sorted
+// multiset.  Every warp of the group takes the percentiles k = gw, gw + gwarps, ..: level 1 on the
+// high-byte counts (each warp for itself: two 128-bit loads and one scan), then one 1 KB slice of the table
+// per rank.  No shared scratch: the lane that holds a rank hands its answer round with shuffles.
+__device__ __forceinline__ int k2_locate8(const int (&c)[8], int rel) {      // t with sum(c[<t]) <= rel < sum(c[<=t])
+    int t = 0, run = 0;
 #pragma unroll
-    for (int i = 0; i < kK2Vec; ++i)
-        if (gt + i * gthreads < nfull) {
-            k2_range<MASKED>(vreg[i], mreg[i], mn2, mx2);
-            if (MASKED) any |= (mreg[i].x | mreg[i].y) != 0u;
-        }
-    for (int idx = gt + kK2Vec * gthreads; idx < nfull; idx += gthreads) {
-        const uint4 v = ld_reuse(px4 + idx);
-        uint2 m = make_uint2(0u, 0u);
-        if (MASKED) { m = __ldg(mk2 + idx); any |= (m.x | m.y) != 0u; }
-        k2_range<MASKED>(v, m, mn2, mx2);
-    }
-    if (gt < rem) {
-        const int i = nfull * 8 + gt;
-        if (!MASKED || T.mk[i] != 0) {
-            const uint32_t x = T.px[i];
-            mn2 = __vminu2(mn2, x | 0xffff0000u);
-            mx2 = __vmaxu2(mx2, x);
-            any = true;
-        }
-    }
-    const bool have = (gt < nfull || gt < rem) && any;      // this lane saw at least one valid pixel
-    uint32_t lo = have ? min(mn2 & 0xffffu, mn2 >> 16) : 0xffffu;
-    uint32_t hi = have ? max(mx2 & 0xffffu, mx2 >> 16) : 0u;
-    lo = __reduce_min_sync(0xffffffffu, lo);
-    hi = __reduce_max_sync(0xffffffffu, hi);
-    if ((gt & 31) == 0 && lo <= hi) {
-        const uint32_t b0 = lo >> 6, b1 = hi >> 6;
-        for (uint32_t s = b0 >> 5; s <= (b1 >> 5); ++s) {
-            const uint32_t from = s == (b0 >> 5) ? (b0 & 31u) : 0u, to = s == (b1 >> 5) ? (b1 & 31u) : 31u;
-            const uint32_t bits = (0xffffffffu >> (31u - to)) & (0xffffffffu << from);
-            if ((coarse[s] & bits) != bits) atomicOr(&coarse[s], bits);
-        }
-    }
+    for (int u = 0; u < 7; ++u) { run += c[u]; t += rel >= run ? 1 : 0; }
+    return t;
 }
-
-// One warp: numpy percentile (method "linear") from the histogram; ranks are 0-based positions
-// in the sorted multiset.
-__device__ __forceinline__ void k2_percentiles(K2Smem& S, const uint32_t* coarse, int* vals, const Params& P,
-                                               int n, double* o) {
+__device__ __forceinline__ void k2_percentiles(const K2Smem& S, const K2Group& G, const Params& P, int n, double* o,
+                                               int gw, int gwarps) {
     const int lane = threadIdx.x & 31;
-    int lo[9], hi[9], maxrank = 0;
+    // level 1: lane l holds the counts of the slices 8l .. 8l+7
+    const uint4* c4 = reinterpret_cast<const uint4*>(G.c256);
+    const uint4 qa = c4[2 * lane], qb = c4[2 * lane + 1];
+    const int c[8] = {(int)qa.x, (int)qa.y, (int)qa.z, (int)qa.w, (int)qb.x, (int)qb.y, (int)qb.z, (int)qb.w};
+    const int tot = c[0] + c[1] + c[2] + c[3] + c[4] + c[5] + c[6] + c[7];
+    int incl = tot;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
+    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o2);
+        if (lane >= o2) incl += v;
+    }
+    const int excl = incl - tot;
+    for (int k = gw; k < 9; k += gwarps) {
         const double virt = __dmul_rn((double)(n - 1), P.quant[k]);
-        if (virt >= (double)(n - 1)) { lo[k] = hi[k] = n - 1; }
-        else { lo[k] = (int)floor(virt); hi[k] = lo[k] + 1; }
-        maxrank = max(maxrank, hi[k]);
-    }
-    int cum = 0;
-    bool done = false;
-    for (int cw = 0; cw < 32 && !done; ++cw) {
-        uint32_t bits = coarse[cw];
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const int block = cw * 32 + b;
-            const uint32_t wv = S.hist[block * 32 + lane];
-            const int c0 = wv & 0xffffu, c1 = wv >> 16, tot = c0 + c1;
-            int incl = tot;
+        int rk[2];
+        if (virt >= (double)(n - 1)) { rk[0] = rk[1] = n - 1; }
+        else { rk[0] = (int)floor(virt); rk[1] = rk[0] + 1; }
+        int val[2], sl_prev = -1;
+        int d[8] = {0, 0, 0, 0, 0, 0, 0, 0}, in2 = 0, tl = 0;
 #pragma unroll
-            for (int o2 = 1; o2 < 32; o2 <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o2);
-                if (lane >= o2) incl += v;
-            }
-            const int r0 = cum + incl - tot, r1 = cum + incl;
-            const int base = block * 64 + 2 * lane;
+        for (int j = 0; j < 2; ++j) {
+            // the lane whose eight slices hold the rank
+            const uint32_t own = __ballot_sync(0xffffffffu, rk[j] >= excl && rk[j] < incl);
+            const int src = __ffs(own) - 1;
+            const int t1 = k2_locate8(c, rk[j] - excl);
+            int below = excl;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                if (lo[k] >= r0 && lo[k] < r1) vals[2 * k] = base + (lo[k] >= r0 + c0);
-                if (hi[k] >= r0 && hi[k] < r1) vals[2 * k + 1] = base + (hi[k] >= r0 + c0);
+            for (int u = 0; u < 7; ++u) below += u < t1 ? c[u] : 0;
+            const int sl = __shfl_sync(0xffffffffu, 8 * lane + t1, src);
+            const int base = __shfl_sync(0xffffffffu, below, src);       // pixels in the slices below
+            if (sl != sl_prev) {                           // level 2: lane l holds the values 8l .. 8l+7 of the slice
+                const uint4 q = reinterpret_cast<const uint4*>(S.hist)[sl * 32 + lane];
+                d[0] = (int)(q.x & 0xffffu); d[1] = (int)(q.x >> 16); d[2] = (int)(q.y & 0xffffu); d[3] = (int)(q.y >> 16);
+                d[4] = (int)(q.z & 0xffffu); d[5] = (int)(q.z >> 16); d[6] = (int)(q.w & 0xffffu); d[7] = (int)(q.w >> 16);
+                tl = d[0] + d[1] + d[2] + d[3] + d[4] + d[5] + d[6] + d[7];
+                in2 = tl;
+#pragma unroll
+                for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, in2, o2);
+                    if (lane >= o2) in2 += v;
+                }
+                sl_prev = sl;
             }
-            cum += __shfl_sync(0xffffffffu, incl, 31);
-            if (cum > maxrank) { done = true; break; }
+            const int r1 = base + in2, r0 = r1 - tl;
+            const uint32_t own2 = __ballot_sync(0xffffffffu, rk[j] >= r0 && rk[j] < r1);
+            const int t2 = k2_locate8(d, rk[j] - r0);
+            val[j] = __shfl_sync(0xffffffffu, sl * 256 + 8 * lane + t2, __ffs(own2) - 1);
         }
-    }
-    __syncwarp();
-    if (lane < 9) {
-        const double virt = __dmul_rn((double)(n - 1), P.quant[lane]);
-        const double g = virt - floor(virt);
-        const int a = vals[2 * lane], b = vals[2 * lane + 1];
-        const double diff = (double)(b - a);
-        // numpy _lerp: a + diff*t, replaced by b - diff*(1-t) where t >= 0.5 (no FMA there)
-        const double r = (g >= 0.5) ? __dsub_rn((double)b, __dmul_rn(diff, __dsub_rn(1.0, g)))
-                                    : __dadd_rn((double)a, __dmul_rn(diff, g));
-        o[1 + lane] = r;
+        if (lane == 0) {
+            const double g = virt - floor(virt);
+            const int a = val[0], b = val[1];
+            const double diff = (double)(b - a);
+            // numpy _lerp: a + diff*t, replaced by b - diff*(1-t) where t >= 0.5 (no FMA there)
+            o[1 + k] = (g >= 0.5) ? __dsub_rn((double)b, __dmul_rn(diff, __dsub_rn(1.0, g)))
+                                  : __dadd_rn((double)a, __dmul_rn(diff, g));
+        }
     }
 }
 
@@ -260,7 +223,7 @@ __global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_
     K2Group& G = S.grp[g];
 
     for (int k = tid; k < 32768; k += blockDim.x) S.hist[k] = 0u;
-    if (gt < 32) G.coarse[gt] = 0u;
+    for (int k = gt; k < 256; k += gthreads) G.c256[k] = 0u;
     if (tid < 32) S.dummy[tid] = 0u;
     if (gt == 0) { G.constant = 0; G.cnt = 0u; }
     for (int k = tid; k < kK2GfixSmem; k += blockDim.x) S.gfix[k] = __ldg(P.gfix + k);
@@ -310,22 +273,28 @@ __global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_
         double* o = nullptr;
         if (active) {
             o = T.out_row + P.col_basic + kNBasic * T.slot;
-            k2_mark_walk<MASKED>(G.coarse, T, gt, gthreads, vreg, mreg);   // table-free
+            // the tile's pixels must have landed BEFORE the table is taken: a group that waits for HBM while it
+            // holds the table stalls the three others (an empty asm that reads a register waits for its load)
+#pragma unroll
+            for (int i = 0; i < kK2Vec; ++i) {
+                asm volatile("" ::"r"(vreg[i].x), "r"(vreg[i].y), "r"(vreg[i].z), "r"(vreg[i].w));
+                if (MASKED) asm volatile("" ::"r"(mreg[i].x), "r"(mreg[i].y));
+            }
         }
         ring_acquire(R);                                   // ---- table owned by this group ----
         int n = 0;
         if (active) {
-            k2_walk<0, MASKED>(S, P, T, gt, gthreads, vreg, mreg, cnt, maxold, acc, olds);
+            k2_walk<0, MASKED>(S, G.c256, P, T, gt, gthreads, vreg, mreg, cnt, maxold, acc, olds);
             if (MASKED) {
                 cnt = __reduce_add_sync(0xffffffffu, cnt);
                 if (lane == 0 && cnt) atomicAdd(&G.cnt, cnt);
             }
             ring_group_sync(R);                            // histogram complete
             n = MASKED ? (int)G.cnt : T.n;
-            if (gw == 0 && n > 0) k2_percentiles(S, G.coarse, G.vals, P, n, o);
-            ring_group_sync(R);                            // percentile walk done, n read by everyone
-            k2_walk<2, MASKED>(S, P, T, gt, gthreads, vreg, mreg, cnt, maxold, acc);
-            if (gt < 32) G.coarse[gt] = 0u;
+            if (n > 0) k2_percentiles(S, G, P, n, o, gw, R.gwarps);
+            ring_group_sync(R);                            // percentiles done, n read by everyone
+            k2_walk<2, MASKED>(S, G.c256, P, T, gt, gthreads, vreg, mreg, cnt, maxold, acc);
+            for (int k = gt; k < 256; k += gthreads) G.c256[k] = 0u;
             if (gt == 0) G.cnt = 0u;
         }
         ring_release(R);                                   // ---- hand the table to the next group ----
@@ -336,6 +305,16 @@ __global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_
         walk.next();
         active = (long long)ng * (it + 1) + g < mine;
         if (active) { T = resolve_k((long long)ng * (it + 1) + g); fetch(T); }
+        if (worklist && (long long)ng * (it + 2) + g < mine) {
+            // the tile after next: pull it into L2 now (worklist tiles come in no order; their first touch is HBM latency)
+            const Tile T2 = resolve_tile(P, (long long)worklist[first + ((long long)ng * (it + 2) + g) * gridDim.x]);
+            const int lpx = (T2.n * 2 + 127) >> 7, lmk = MASKED ? (T2.n + 127) >> 7 : 0;     // 128-byte lines
+            for (int l = gt; l < lpx + lmk; l += gthreads) {
+                const char* line = l < lpx ? reinterpret_cast<const char*>(T2.px) + 128 * l
+                                           : reinterpret_cast<const char*>(T2.mk) + 128 * (l - lpx);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+            }
+        }
 
         if (was_active) {
             // entropy terms of the register-resident pixels: G[old], looked up off the critical path

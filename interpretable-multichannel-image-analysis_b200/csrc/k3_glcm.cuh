@@ -48,16 +48,20 @@ struct alignas(16) K3Geom {
     int nrows, r0, c0, c1, ipr, items, w, doff;
     float rcp;                                     // 1 / ipr: row = floor((item + 0.5) * rcp), exact for item < 2^20
     int aligned, base_j, ws, sb;                   // aligned path: which side is 16-byte aligned; word / bit shift of the other
+                                                   // masked tiles: sb = byte offset of pixel (r0, 0) in the staged rows
     int pad[3];
 };
 static_assert(sizeof(K3Geom) == 64, "four 128-bit shared-memory loads");
 
-// What the front kernel (K3a) leaves for the bins kernel (K3b) per tile: this header, then the quantised
-// pixels, then the mask bits -- one contiguous record of the scratch buffer, fetched with one bulk copy.
+// What the front kernel (K3a) leaves for the bins kernel (K3b) per tile: this header, then the mask bits (all
+// rows), then the quantised pixels of the rows the mask's bounding box spans -- one contiguous record of the
+// scratch buffer, fetched with one bulk copy of `len` bytes (a mask that covers a tenth of a 128x128 tile makes
+// a 5 KB record, not 19 KB; the lengths are kept in a table behind the records, because the bins kernel must
+// know them before it fetches).
 struct alignas(16) K3Hdr {
     K3Geom geom[kMaxAngles];                       // pad[0] = number of pairs of that direction
     uint32_t* rec;                                 // the tile's first record (direction 0) in the output row
-    uint32_t tile, pad;
+    uint32_t tile, len;                            // len: bytes of this record that are in use (multiple of 16)
 };
 static_assert(sizeof(K3Hdr) == 272, "multiple of 16 bytes");
 __host__ __device__ inline size_t k3_rec_bytes(int max_pixels, bool masked) {
@@ -68,6 +72,7 @@ struct alignas(16) K3Smem {                     // behind the table (64 or 32 KB
     uint32_t part[2][kK3MaxWarps][2];           // per direction parity and warp: sum of squares, counts taken back
     unsigned long long mbar[2];                 // completion of the bulk copy into record buffer 0 / 1
     uint32_t tq[4];                             // local tile indices drawn from the global counter
+    uint32_t tlen[4];                           // ... and the lengths of their records
     uint32_t slow[4];                           // fallback: sum of squares, [1] dense count check of the dump, [2] counts taken back
 };
 struct K3Group {                               // where the quantised tile and its mask bits live
@@ -134,7 +139,7 @@ __host__ __device__ inline int k3_q8_capacity(int hs, int ws, bool masked) { ret
 // Pairs (r, c) -> (r + dr, c + dc) with both pixels inside the box rows [br0, br1], columns
 // [bc0, bc1] (the whole tile, or the bounding box of the mask: pairs outside it cannot exist).
 template <bool MASKED, int NG>
-__device__ __forceinline__ K3Geom k3_geom(int w, int dr, int dc, int br0, int br1, int bc0, int bc1) {
+__device__ __forceinline__ K3Geom k3_geom(int w, int dr, int dc, int br0, int br1, int bc0, int bc1, int qbias) {
     K3Geom G;
     const int pitch = k3_pitch<MASKED>(w);
     G.r0 = br0;
@@ -143,7 +148,7 @@ __device__ __forceinline__ K3Geom k3_geom(int w, int dr, int dc, int br0, int br
     G.c1 = bc1 + 1 - (dc > 0 ? dc : 0);
     G.w = pitch;                                   // quantised pixels: row pitch and pair offset in bytes
     G.doff = dr * pitch + dc;
-    G.aligned = 0; G.base_j = dc < 0; G.ws = 0; G.sb = 0;
+    G.aligned = 0; G.base_j = dc < 0; G.ws = 0; G.sb = MASKED ? br0 * pitch - qbias : 0;
     G.pad[0] = 0; G.pad[1] = w; G.pad[2] = dr * w + dc;      // mask bits stay compact: their row pitch and pair offset
     if (G.nrows <= 0 || G.c1 <= G.c0) { G.items = 0; G.ipr = 1; G.rcp = 1.0f; G.nrows = 0; return G; }
     // unmasked tiles only: the aligned side starts at column bc0 = 0.  (Widening a mask's bounding box to the
@@ -184,7 +189,7 @@ __device__ __forceinline__ bool k3_item(const K3Group& Gp, const K3Geom& G, int 
         c = G.c0 + NP * (item - r * G.ipr);
     }
     const int nv = min(NP, G.c1 - c);
-    const int oi = (G.r0 + r) * G.w + c, oj = oi + G.doff;
+    const int oi = MASKED ? G.sb + r * G.w + c : (G.r0 + r) * G.w + c, oj = oi + G.doff;
     pm = ((1u << NP) - 1u) >> (NP - nv);
     if (!MASKED && NG == 4 && G.aligned) {
         const int ob = G.base_j ? oj : oi, oo = G.base_j ? oi : oj;      // ob is a multiple of 16
@@ -204,7 +209,11 @@ __device__ __forceinline__ bool k3_item(const K3Group& Gp, const K3Geom& G, int 
     }
     if (MASKED) {
         const int mi = (G.r0 + r) * G.pad[1] + c;
+#ifdef IMFEAT_EXP_NOMASKBITS
+        pm &= Gp.mbits[mi >> 5] | 0xffu;
+#else
         pm &= k3_bits(Gp.mbits, mi) & k3_bits(Gp.mbits, mi + G.pad[2]);
+#endif
         if (pm == 0u) return false;
     }
     const uint32_t* bi = Gp.q8 + (oi >> 2);
@@ -234,6 +243,9 @@ __device__ __forceinline__ void k3_sums(const double* homtab, uint32_t I4, uint3
     A.sij = __dp4a(I4, J4, A.sij);
     A.sd += __vsadu4(I4, J4);
     const uint32_t D4 = __vabsdiffu4(I4, J4);
+#ifdef IMFEAT_EXP_NOHOM
+    A.hom0 += (double)D4; return;
+#endif
     A.hom0 += homtab[D4 & 0xffu];                  // two chains: a DADD waits several cycles for the one before it
     A.hom1 += homtab[(D4 >> 8) & 0xffu];
     A.hom0 += homtab[(D4 >> 16) & 0xffu];
@@ -439,9 +451,10 @@ k3a_front_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t tile
     unsigned char* mine = k3a_smem_raw + (size_t)warp * k3a_warp_bytes(max_pixels, MASKED);
     K3Hdr& H = *reinterpret_cast<K3Hdr*>(mine);
     K3Group Gp;
-    Gp.q8 = reinterpret_cast<uint32_t*>(mine + sizeof(K3Hdr));
-    Gp.mbits = Gp.q8 + k3_q8_words(max_pixels);
+    Gp.mbits = reinterpret_cast<uint32_t*>(mine + sizeof(K3Hdr));
+    Gp.q8 = Gp.mbits + k3_mb_words(max_pixels, MASKED);
     uint32_t* recs = reinterpret_cast<uint32_t*>(mine + rec_bytes);      // [n_angles][kK3Rec]
+    uint32_t* const rec_len = reinterpret_cast<uint32_t*>(scratch + (size_t)n_local * rec_bytes);
     for (int k = threadIdx.x; k < 256; k += blockDim.x) homtab[k] = 1.0 / (1.0 + (double)(k * k));
     __syncthreads();
     const bool k1_max = P.col_basic >= 0;
@@ -490,7 +503,7 @@ k3a_front_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t tile
             if (!fast) k3_magic(vmax, mul, sh);
         }
 
-        // ---- stage the tile: 8-bit quantisation, mask bits + bounding box ----
+        // ---- stage the tile: mask bits + bounding box first, then the 8-bit quantisation of the rows the box spans ----
         int brmin = 1 << 30, brmax = -1, bcmin = 1 << 30, bcmax = -1;
         const float rtw = __frcp_rn((float)tw);
         auto mask_chunk = [&](int idx, const uint2& m) {
@@ -511,7 +524,41 @@ k3a_front_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t tile
                 }
             }
         };
+        if (MASKED) {
+            constexpr int kUm = 8;                         // mask loads in flight per lane
+            int idx = lane;
+            for (; idx + 32 * (kUm - 1) < nfull; idx += 32 * kUm) {
+                uint2 m[kUm];
+#pragma unroll
+                for (int u = 0; u < kUm; ++u) m[u] = __ldg(mk2 + idx + 32 * u);
+#pragma unroll
+                for (int u = 0; u < kUm; ++u) mask_chunk(idx + 32 * u, m[u]);
+            }
+            for (; idx < nfull; idx += 32) mask_chunk(idx, __ldg(mk2 + idx));
+            if (lane == 0 && rem) {                        // tail pixels (< 8): one lane, in order
+                uint32_t bits = 0u;
+                for (int k = 0; k < rem; ++k) {
+                    const int i = nfull * 8 + k;
+                    if (T.mk[i] != 0) {
+                        bits |= 1u << k;
+                        const int ra = i / tw, ca = i - ra * tw;
+                        brmin = min(brmin, ra); brmax = max(brmax, ra); bcmin = min(bcmin, ca); bcmax = max(bcmax, ca);
+                    }
+                }
+                mbytes[nfull] = (uint8_t)bits;
+            }
+            brmin = __reduce_min_sync(0xffffffffu, brmin); brmax = __reduce_max_sync(0xffffffffu, brmax);
+            bcmin = __reduce_min_sync(0xffffffffu, bcmin); bcmax = __reduce_max_sync(0xffffffffu, bcmax);
+            if (brmax < 0) { brmin = 0; bcmin = 0; bcmax = -1; }           // empty mask: nothing to stage, no pair
+        } else {
+            brmin = 0; brmax = th - 1; bcmin = 0; bcmax = tw - 1;
+        }
         const int pitch = k3_pitch<MASKED>(tw), cpr = tw >> 3;         // padded pitch: 8-pixel chunks per row
+        // the staged rows: pixel (r, c) lies at byte r * pitch + c - qbias of the quantised block
+        const int p_lo = brmin * tw, p_hi = (brmax + 1) * tw;
+        const int i0 = p_lo >> 3, i1 = min(nfull, (p_hi + 7) >> 3);
+        const int qbias = pitch == tw ? (p_lo & ~7) : brmin * pitch;
+        const uint32_t q8_used = (uint32_t)((pitch == tw ? p_hi : (brmax + 1) * pitch) - qbias);
         const float rcpr = __frcp_rn((float)max(cpr, 1));
         auto quant_chunk = [&](int idx, const uint4& v) {              // out-of-mask pixels may exceed the maximum:
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};               // their bytes are never part of a pair
@@ -527,63 +574,37 @@ k3a_front_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t tile
             }
             const uint32_t lo = __byte_perm(q[0], q[1], 0x5410), hi = __byte_perm(q[2], q[3], 0x5410);
             if (pitch == tw) {
-                *reinterpret_cast<uint2*>(Gp.q8 + 2 * idx) = make_uint2(lo, hi);
+                *reinterpret_cast<uint2*>(Gp.q8 + 2 * idx - (qbias >> 2)) = make_uint2(lo, hi);
             } else {                                       // the chunk lies inside one row (tw % 8 == 0)
                 const int ra = (int)(((float)idx + 0.5f) * rcpr);
-                uint32_t* dst = Gp.q8 + ((ra * pitch) >> 2) + 2 * (idx - ra * cpr);
+                uint32_t* dst = Gp.q8 + (((ra - brmin) * pitch) >> 2) + 2 * (idx - ra * cpr);
                 dst[0] = lo; dst[1] = hi;
             }
         };
         {
             constexpr int kU = 4;                          // loads in flight per lane
-            int idx = lane;
-            for (; idx + 32 * (kU - 1) < nfull; idx += 32 * kU) {
+            int idx = i0 + lane;
+            for (; idx + 32 * (kU - 1) < i1; idx += 32 * kU) {
                 uint4 v[kU];
-                uint2 m[kU];
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    v[u] = k1_max ? ld_stream(px4 + idx + 32 * u) : ld_reuse(px4 + idx + 32 * u);
-                    if (MASKED) m[u] = __ldg(mk2 + idx + 32 * u);
-                }
+                for (int u = 0; u < kU; ++u) v[u] = k1_max ? ld_stream(px4 + idx + 32 * u) : ld_reuse(px4 + idx + 32 * u);
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    quant_chunk(idx + 32 * u, v[u]);
-                    if (MASKED) mask_chunk(idx + 32 * u, m[u]);
-                }
+                for (int u = 0; u < kU; ++u) quant_chunk(idx + 32 * u, v[u]);
             }
-            for (; idx < nfull; idx += 32) {
-                quant_chunk(idx, ld_reuse(px4 + idx));
-                if (MASKED) mask_chunk(idx, __ldg(mk2 + idx));
-            }
+            for (; idx < i1; idx += 32) quant_chunk(idx, ld_reuse(px4 + idx));
         }
-        if (lane < rem) {
+        if (lane < rem && p_hi > nfull * 8) {
             const int i = nfull * 8 + lane;
             const uint32_t qv = fast ? __umulhi((uint32_t)T.px[i], mul) : k3_quant(T.px[i], mul, sh);
-            reinterpret_cast<uint8_t*>(Gp.q8)[i] = (uint8_t)qv;
-        }
-        if (MASKED) {
-            if (lane == 0 && rem) {                        // tail pixels (< 8): one lane, in order
-                uint32_t bits = 0u;
-                for (int k = 0; k < rem; ++k) {
-                    const int i = nfull * 8 + k;
-                    if (T.mk[i] != 0) {
-                        bits |= 1u << k;
-                        const int ra = i / tw, ca = i - ra * tw;
-                        brmin = min(brmin, ra); brmax = max(brmax, ra); bcmin = min(bcmin, ca); bcmax = max(bcmax, ca);
-                    }
-                }
-                mbytes[nfull] = (uint8_t)bits;
-            }
-            brmin = __reduce_min_sync(0xffffffffu, brmin); brmax = __reduce_max_sync(0xffffffffu, brmax);
-            bcmin = __reduce_min_sync(0xffffffffu, bcmin); bcmax = __reduce_max_sync(0xffffffffu, bcmax);
-        } else {
-            brmin = 0; brmax = th - 1; bcmin = 0; bcmax = tw - 1;
+            reinterpret_cast<uint8_t*>(Gp.q8)[i - qbias] = (uint8_t)qv;
         }
         // geometry of the directions: lane a works out direction a
-        if (lane < P.n_angles) H.geom[lane] = k3_geom<MASKED, NG>(tw, P.dr[lane], P.dc[lane], brmin, brmax, bcmin, bcmax);
+        if (lane < P.n_angles) H.geom[lane] = k3_geom<MASKED, NG>(tw, P.dr[lane], P.dc[lane], brmin, brmax, bcmin, bcmax, qbias);
+        const uint32_t len = ((uint32_t)sizeof(K3Hdr) + 4u * (uint32_t)k3_mb_words(max_pixels, MASKED) + q8_used + 15u) & ~15u;
         if (lane == 0) {
             H.rec = reinterpret_cast<uint32_t*>(T.out_row + P.col_glcm + T.slot * P.n_angles * kNGlcm);
-            H.tile = tile_base + tl; H.pad = 0u;
+            H.tile = tile_base + tl; H.len = len;
+            rec_len[tl] = len;
         }
         __syncwarp();
 
@@ -627,7 +648,7 @@ k3a_front_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t tile
         {
             const uint4* src = reinterpret_cast<const uint4*>(mine);
             uint4* dst = reinterpret_cast<uint4*>(scratch + (size_t)tl * rec_bytes);
-            for (int k = lane; k < (int)(rec_bytes >> 4); k += 32) dst[k] = src[k];
+            for (int k = lane; k < (int)(len >> 4); k += 32) dst[k] = src[k];
         }
         __syncwarp();                                      // the buffers are rewritten by the next tile
     }
@@ -653,6 +674,7 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t n_loca
     const uint32_t rec_bytes = (uint32_t)k3_rec_bytes(max_pixels, MASKED);
     unsigned char* recbuf0 = k3_smem_raw + TB * 1024 + sizeof(K3Smem);
     const uint32_t hist_addr = smem_addr(hist), bar0 = smem_addr(&S.mbar[0]), rec_addr0 = smem_addr(recbuf0);
+    const uint32_t* const rec_len = reinterpret_cast<const uint32_t*>(scratch + (size_t)n_local * rec_bytes);
 
     for (int k = tid; k < TB * 256; k += NT) hist[k] = 0u;
     if (tid == 0) {
@@ -660,6 +682,8 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t n_loca
         // tail does not depend on how many CTAs are resident at once), drawn two tiles ahead
         S.tq[0] = blockIdx.x;
         S.tq[1] = gridDim.x + atomicAdd(P.sched + 6, 1u);
+        S.tlen[0] = blockIdx.x < n_local ? rec_len[blockIdx.x] : 0u;
+        S.tlen[1] = S.tq[1] < n_local ? rec_len[S.tq[1]] : 0u;
         S.slow[0] = 0u; S.slow[1] = 0u; S.slow[2] = 0u;
         mbar_init(bar0, 1);
         mbar_init(bar0 + 8, 1);
@@ -668,12 +692,12 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t n_loca
     __syncthreads();
     // the record of a tile (header, quantised pixels, mask bits) arrives with one bulk copy (1-D TMA) in one of two
     // buffers: the record of tile j + 1 travels while tile j is worked off
-    auto fetch = [&](uint32_t tl, uint32_t b) {              // thread 0
+    auto fetch = [&](uint32_t tl, uint32_t b, uint32_t len) { // thread 0
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // earlier generic reads of the buffer vs the async write
-        mbar_expect_tx(bar0 + 8 * b, rec_bytes);
-        bulk_g2s(rec_addr0 + b * rec_bytes, scratch + (size_t)tl * rec_bytes, rec_bytes, bar0 + 8 * b);
+        mbar_expect_tx(bar0 + 8 * b, len);
+        bulk_g2s(rec_addr0 + b * rec_bytes, scratch + (size_t)tl * rec_bytes, len, bar0 + 8 * b);
     };
-    if (tid == 0 && blockIdx.x < n_local) fetch(blockIdx.x, 0u);
+    if (tid == 0 && blockIdx.x < n_local) fetch(blockIdx.x, 0u, S.tlen[0]);
     uint32_t dcount = 0u;                        // directions done by this CTA: its parity picks the partial-sum bank
     int prefer_wide = 0;                         // TB = 32: directions left that skip the 4-bit attempt
 
@@ -681,16 +705,17 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t n_loca
         const uint32_t tl = S.tq[j & 3u];
         if (tl >= n_local) break;
         const uint32_t b = j & 1u;
-        uint32_t t_draw = 0u;
+        uint32_t t_draw = 0u, len_draw = 0u;
         if (tid == 0) {
             t_draw = gridDim.x + atomicAdd(P.sched + 6, 1u);
             const uint32_t t_next = S.tq[(j + 1) & 3u];
-            if (t_next < n_local) fetch(t_next, b ^ 1u);     // that buffer's tile (j - 1) was finished before the last barrier
+            if (t_next < n_local) fetch(t_next, b ^ 1u, S.tlen[(j + 1) & 3u]);     // that buffer's tile (j - 1) was finished before the last barrier
+            if (t_draw < n_local) len_draw = rec_len[t_draw];
         }
         const K3Hdr& H = *reinterpret_cast<const K3Hdr*>(recbuf0 + b * rec_bytes);
         K3Group Gp;
-        Gp.q8 = reinterpret_cast<uint32_t*>(recbuf0 + b * rec_bytes + sizeof(K3Hdr));
-        Gp.mbits = Gp.q8 + k3_q8_words(max_pixels);
+        Gp.mbits = reinterpret_cast<uint32_t*>(recbuf0 + b * rec_bytes + sizeof(K3Hdr));
+        Gp.q8 = Gp.mbits + k3_mb_words(max_pixels, MASKED);
         mbar_wait(bar0 + 8 * b, (j >> 1) & 1u);            // ---- record landed ----
 
 #pragma unroll 1
@@ -763,13 +788,13 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t n_loca
                 sq = __reduce_add_sync(0xffffffffu, sq);
                 cnt = __reduce_add_sync(0xffffffffu, cnt);
                 if (lane == 0) { S.part[par][warp][0] = sq; S.part[par][warp][1] = cnt; }
-                if (tid == 0 && a + 1 == P.n_angles) S.tq[(j + 2) & 3u] = t_draw;
+                if (tid == 0 && a + 1 == P.n_angles) { S.tq[(j + 2) & 3u] = t_draw; S.tlen[(j + 2) & 3u] = len_draw; }
                 __syncthreads();                           // ---- table clean, sums complete ----
 #pragma unroll
                 for (int w = 0; w < NW; ++w) { sqt += S.part[par][w][0]; cntt += S.part[par][w][1]; }
             } else {
                 --prefer_wide;
-                if (tid == 0 && a + 1 == P.n_angles) S.tq[(j + 2) & 3u] = t_draw;
+                if (tid == 0 && a + 1 == P.n_angles) { S.tq[(j + 2) & 3u] = t_draw; S.tlen[(j + 2) & 3u] = len_draw; }
                 cntt = M + 1u;                             // straight to the wider counters
             }
             if (cntt != M) {

@@ -27,6 +27,7 @@ for r in rows:
         tot_i += inst
         tot_s += samp
 print("total instructions %d  (%.1f per unit)  samples %d" % (tot_i, tot_i / norm, tot_s))
-for inst, samp, f, ln, src in sorted(lines, reverse=True)[:top]:
+key = (lambda t: t[1]) if (len(sys.argv) > 5 and sys.argv[5] == "stall") else (lambda t: t[0])
+for inst, samp, f, ln, src in sorted(lines, key=key, reverse=True)[:top]:
     print("%8.1f %5.1f%% inst | %5.1f%% stall | %s:%d  %s" % (inst / norm, 100.0 * inst / tot_i,
                                                            100.0 * samp / max(tot_s, 1), f, ln, src[:95]))
