@@ -157,8 +157,8 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
         ctx->env_k1_tma = flag("IMFEAT_K1_TMA", 0);        // 1: K1 through the cp.async.bulk ring (unmasked)
         ctx->env_k2_compact = flag("IMFEAT_K2_COMPACT", 1); // 0: every tile through the full-range ring kernel
         ctx->env_k4_warp = flag("IMFEAT_K4_WARP", 1);       // 0: CTA-per-tile K4 for every batch
-        const int g2 = flag("IMFEAT_K2_GROUPS", 4);
-        ctx->env_k2_groups = (g2 == 2 || g2 == 4 || g2 == 8) ? g2 : 4;
+        const int g2 = flag("IMFEAT_K2_GROUPS", 2);
+        ctx->env_k2_groups = (g2 == 2 || g2 == 4 || g2 == 8) ? g2 : 2;
         ctx->env_k3_threads = flag("IMFEAT_K3_THREADS", 128) == 256 ? 256 : 128;   // threads per K3 CTA
         ctx->env_k3_chunk = flag("IMFEAT_K3_CHUNK", 16384);                        // objects per front/bins round of K3
         if (ctx->env_k3_chunk < 1) ctx->env_k3_chunk = 16384;

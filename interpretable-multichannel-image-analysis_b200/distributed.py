@@ -176,16 +176,27 @@ class ShardedTable:
         return self.table
 
 
-def slab_bounds(n_rows, slab_rows):
-    """[(a, b)] covering [0, n_rows) in slabs of slab_rows."""
+def slab_bounds(n_rows, slab_rows, tail_rows=None):
+    """[(a, b)] covering [0, n_rows) in slabs of slab_rows.  With ``tail_rows`` the last slab is halved again and
+    again down to about that size: the delivery of the LAST slab is the only one no computation hides, so it
+    should be small (a 16,384-row slab of 720 columns is 94 MB per peer, a 2,048-row one 12 MB)."""
     if n_rows <= 0:
         return []
     slab_rows = max(1, int(slab_rows))
-    return [(a, min(n_rows, a + slab_rows)) for a in range(0, n_rows, slab_rows)]
+    bounds = [(a, min(n_rows, a + slab_rows)) for a in range(0, n_rows, slab_rows)]
+    if tail_rows:
+        tail_rows = max(1, int(tail_rows))
+        a, b = bounds.pop()
+        while b - a > 2 * tail_rows:
+            mid = a + (b - a + 1) // 2
+            bounds.append((a, mid))
+            a = mid
+        bounds.append((a, b))
+    return bounds
 
 
 def extract_sharded(extractor, planes, masks=None, sizes=None, hs=None, ws=None, n_objects=None, table=None,
-                    slab_objects=16384, group=None, transport=None, finish=True):
+                    slab_objects=16384, group=None, transport=None, finish=True, tail_objects=2048):
     """Extract this rank's shard slab by slab and deliver every slab to all ranks while the next one is computed.
 
     planes / masks / sizes : this rank's shard, as ``FeatureExtractor.extract_planar`` takes them
@@ -193,7 +204,9 @@ def extract_sharded(extractor, planes, masks=None, sizes=None, hs=None, ws=None,
     n_objects              : total over all ranks (rank r holds objects shard_range(n_objects, world, r))
     table                  : a ``ShardedTable`` to reuse (its mappings are set up once); made here when None
     Returns the ShardedTable; ``table.table`` is the float64 [n_objects, F] table, complete on every rank once
-    ``finish()`` has returned (called here unless finish=False).  All ranks must pass the same slab_objects.
+    ``finish()`` has returned (called here unless finish=False).  All ranks must pass the same slab_objects and
+    tail_objects (the last slab is split down to about tail_objects rows so that little is left to deliver
+    when the kernels are done; None: no split).
     """
     import torch
     import torch.distributed as dist
@@ -208,7 +221,7 @@ def extract_sharded(extractor, planes, masks=None, sizes=None, hs=None, ws=None,
         table = ShardedTable(n_objects, extractor.row_width(C), device=planes.device, group=group, transport=transport)
     # every rank walks the same slab grid (the collective transport needs matching calls); a rank whose shard is
     # shorter computes fewer rows of its last slabs
-    for a, b in slab_bounds(per, slab_objects):
+    for a, b in slab_bounds(per, slab_objects, tail_objects if world > 1 else None):
         bb = min(b, n_local)
         if bb > a:
             extractor.extract_planar(planes[a:bb], None if masks is None else masks[a:bb],

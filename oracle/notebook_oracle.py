@@ -33,8 +33,19 @@ Pinning status
   scikit-image binary was never run here, so this half is "parity pinned to published
   known answers only".
 * masked statistics, 4-direction GLCM, shape descriptors, spatial moments: the
-  reference has no code for them.  The functions
-  below ARE the specification; "parity unpinned".
+  reference has no code for them, so there is no
+  reference output to compare with.  What pins the functions below instead:
+  - spatial moments (x3) and the region's area, centroid, bounding box, extent and
+    second-order central moments (x2): OpenCV's ``cv2.moments`` / ``cv2.boundingRect``, a
+    third-party implementation of the same published definitions, through the committed
+    fixture ``tests/golden/cv2_moments_golden.npz`` (``tests/golden/make_cv2_golden.py``);
+    major / minor axis and eccentricity follow from those moments by scikit-image's
+    published regionprops formulas;
+  - perimeter (x2): scikit-image's ``measure.perimeter`` restated line by line over the real
+    ``scipy.ndimage`` primitives it calls (``tests/test_oracle_cpu.py``);
+  - 4-direction GLCM (x4): scikit-image's four-angle docstring example;
+  - masked statistics (x1): numpy / scipy on ``x[mask > 0]`` -- the reference's own calls on
+    the selected pixels; a definition, not a comparison: "parity unpinned" for this row.
 """
 from __future__ import annotations
 

@@ -116,6 +116,12 @@ def test_slab_bounds():
     assert D.slab_bounds(0, 4) == []
     assert D.slab_bounds(10, 4) == [(0, 4), (4, 8), (8, 10)]
     assert D.slab_bounds(4, 100) == [(0, 4)]
+    # tapered tail: the last slab is halved down to about tail_rows; the cover stays exact
+    assert D.slab_bounds(16, 16, tail_rows=2) == [(0, 8), (8, 12), (12, 16)]
+    assert D.slab_bounds(10, 4, tail_rows=1) == [(0, 4), (4, 8), (8, 10)]
+    b = D.slab_bounds(125000, 16384, tail_rows=2048)
+    assert b[0] == (0, 16384) and b[-1][1] == 125000 and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+    assert b[-1][1] - b[-1][0] <= 4096 and max(y - x for x, y in b) == 16384
 
 
 def test_shard_ranges_cover_everything():

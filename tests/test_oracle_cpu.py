@@ -145,3 +145,92 @@ def test_quantiser_single_multiply_is_exact():
         q = (x * np.uint64(mul)) >> np.uint64(32)
         ref = ((x.astype(np.float64) / float(vmax)) * 255).astype(np.uint8)
         assert (q == ref).all(), vmax
+
+
+# ---- x2 / x3: the extension blocks against independent third-party implementations ---------------------------
+def _cv2_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cv2_moments_golden.npz"))
+
+
+def test_moments_match_opencv_golden():
+    """x3 (spatial moments): centroid and the seven normalised central moments of the masked plane against
+    OpenCV's cv2.moments (fixture: tests/golden/make_cv2_golden.py).  OpenCV's x is the column, y the row."""
+    from imfeat_b200 import synth
+    g = _cv2_golden()
+    K = {k: i for i, k in enumerate(g["keys"].tolist())}
+    for case, wm in zip(g["cases"].tolist(), g["weighted"]):
+        seed, obj, ch, h, w, shrink = case
+        px, mk = synth.synth_plane(seed, obj, ch, h, w, shrink)
+        got = orc.moment_values(px, mk)
+        want = [wm[K["m01"]] / wm[K["m00"]], wm[K["m10"]] / wm[K["m00"]], wm[K["nu02"]], wm[K["nu11"]], wm[K["nu20"]],
+                wm[K["nu03"]], wm[K["nu12"]], wm[K["nu21"]], wm[K["nu30"]]]
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-13, err_msg=str(case))
+        # the C restatement follows the same definition
+        tab = c_oracle.table(px[None, None].astype(np.uint16), mk[None, None], glcm=False, shape=True, moments=True)
+        np.testing.assert_allclose(tab[0, -9:], want, rtol=1e-9, atol=1e-13, err_msg=str(case))
+        np.testing.assert_allclose(tab[0, -19:-9], orc.shape_values(mk), rtol=1e-9, atol=1e-12, err_msg=str(case))
+
+
+def test_shape_matches_opencv_golden():
+    """x2 (region descriptors): area, centroid, bounding box and extent against OpenCV; major / minor axis and
+    eccentricity from OpenCV's central moments of the mask through scikit-image's published regionprops formulas
+    (inertia tensor [[mu02, -mu11], [-mu11, mu20]] / area, axes 4 sqrt(eigenvalue), ecc = sqrt(1 - l2 / l1))."""
+    from imfeat_b200 import synth
+    g = _cv2_golden()
+    K = {k: i for i, k in enumerate(g["keys"].tolist())}
+    for case, bm, rect in zip(g["cases"].tolist(), g["binary"], g["rect"].tolist()):
+        seed, obj, ch, h, w, shrink = case
+        _, mk = synth.synth_plane(seed, obj, ch, h, w, shrink)
+        got = dict(zip(orc.SHAPE_NAMES, orc.shape_values(mk)))
+        area = bm[K["m00"]]
+        assert got[orc.SHAPE_NAMES[0]] == area == float((mk > 0).sum())
+        vals = orc.shape_values(mk)
+        # order: area, perimeter, bbox_area, extent, centroid_r, centroid_c, major, minor, eccentricity, circularity
+        assert vals[2] == float(rect[2] * rect[3])
+        np.testing.assert_allclose(vals[3], area / float(rect[2] * rect[3]), rtol=1e-15)
+        np.testing.assert_allclose(vals[4], bm[K["m01"]] / area, rtol=1e-12)
+        np.testing.assert_allclose(vals[5], bm[K["m10"]] / area, rtol=1e-12)
+        a, b, c = bm[K["mu20"]] / area, -bm[K["mu11"]] / area, bm[K["mu02"]] / area      # x = column
+        ev = np.linalg.eigvalsh(np.array([[a, b], [b, c]]))
+        l1, l2 = float(ev[1]), max(float(ev[0]), 0.0)
+        np.testing.assert_allclose(vals[6], 4.0 * np.sqrt(l1), rtol=1e-9, err_msg=str(case))
+        np.testing.assert_allclose(vals[7], 4.0 * np.sqrt(l2), rtol=1e-7, atol=1e-9, err_msg=str(case))
+        np.testing.assert_allclose(vals[8], np.sqrt(max(1.0 - l2 / l1, 0.0)), rtol=1e-7, atol=1e-9, err_msg=str(case))
+
+
+def test_perimeter_matches_scipy_ndimage_restatement():
+    """x2 perimeter: scikit-image's measure.perimeter(neighborhood=4) is a few lines over scipy.ndimage
+    (binary_erosion with the 4-connected cross and border_value=0, a 3x3 convolution with weights
+    [[10, 2, 10], [2, 1, 2], [10, 2, 10]], a histogram and a weight table).  Those lines, on the real
+    scipy.ndimage primitives, against the oracle's own erosion / convolution, on masks that touch the border,
+    single pixels, lines, full planes and synthetic ellipses."""
+    from scipy import ndimage as ndi
+    from imfeat_b200 import synth
+
+    def skimage_perimeter(image):
+        strel = np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]], dtype=np.uint8)
+        image = image.astype(np.uint8)
+        eroded = ndi.binary_erosion(image, strel, border_value=0)
+        border = image - eroded
+        weights = np.zeros(50, dtype=np.float64)
+        weights[[5, 7, 15, 17, 25, 27]] = 1
+        weights[[21, 33]] = np.sqrt(2)
+        weights[[13, 23]] = (1 + np.sqrt(2)) / 2
+        conv = ndi.convolve(border, np.array([[10, 2, 10], [2, 1, 2], [10, 2, 10]]), mode="constant", cval=0)
+        return float(np.bincount(conv.ravel(), minlength=50) @ weights)
+
+    rng = np.random.default_rng(5)
+    masks = [np.ones((7, 9), np.uint8), np.zeros((5, 5), np.uint8), np.eye(6, dtype=np.uint8)]
+    one = np.zeros((5, 6), np.uint8); one[2, 3] = 1
+    line = np.zeros((6, 8), np.uint8); line[3, 1:7] = 1
+    masks += [one, line, (rng.random((33, 47)) < 0.6).astype(np.uint8), (rng.random((64, 64)) < 0.9).astype(np.uint8)]
+    masks += [synth.synth_plane(3, k, 0, 64, 64, 256 - 40 * k)[1] for k in range(4)]
+    # a square, exactly: 4 straight sides of the border ring
+    sq = np.zeros((10, 10), np.uint8); sq[2:8, 2:8] = 1
+    masks.append(sq)
+    for m in masks:
+        n1, n2, n3 = orc.perimeter_classes(m)
+        got = n1 + n2 * np.sqrt(2.0) + n3 * (1.0 + np.sqrt(2.0)) / 2.0
+        np.testing.assert_allclose(got, skimage_perimeter(m), rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(orc.shape_values(m)[1], skimage_perimeter(m), rtol=1e-13, atol=1e-13)
