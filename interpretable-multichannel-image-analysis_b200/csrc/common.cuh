@@ -101,6 +101,22 @@ __device__ __forceinline__ long long next_tile(unsigned int* counter) {
     return (long long)__shfl_sync(0xffffffffu, t, 0);
 }
 
+// A warp-per-tile kernel that draws its tiles two ahead can pull the next tile's pixels and mask bytes into L2 while
+// the current tile is worked off.  Measured (round 2): no gain for K12 / K4w / K3a at 20-36 warps per SM (64x64 tiles:
+// 2.98 vs 2.93 ms per step, the extra address arithmetic costs more than the shorter wait saves), but 9 % for the
+// front kernel of K3 on 128x128 strides, where shared memory leaves it 8 warps per SM -- used there only.
+__device__ __forceinline__ void prefetch_tile_l2(const Params& P, long long t, long long t_end) {
+    if (t >= t_end) return;
+    const Tile T = resolve_tile(P, t);
+    const int lane = threadIdx.x & 31;
+    const int lpx = (T.n * 2 + 127) >> 7, lmk = T.mk ? (T.n + 127) >> 7 : 0;      // 128-byte lines
+    for (int l = lane; l < lpx + lmk; l += 32) {
+        const char* line = l < lpx ? reinterpret_cast<const char*>(T.px) + 128 * l
+                                   : reinterpret_cast<const char*>(T.mk) + 128 * (l - lpx);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+    }
+}
+
 // 128-bit streaming load: the tile is read once per kernel, keep it out of L1.
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
     uint4 r;

@@ -339,8 +339,9 @@ static int launch_k3_nt(imfeat_ctx* ctx, bool masked, cudaStream_t st, const Par
         CU(cudaMemsetAsync(P.sched + 5, 0, 2 * sizeof(unsigned int), st));     // the tile counters of the two kernels
         const long long warps_a = (long long)ctx->sm_count * bps_a * kK3aWarps;
         const int grid_a = (int)((nl < warps_a ? nl : warps_a) + kK3aWarps - 1) / kK3aWarps;
-        if (masked) k3a_front_kernel<true><<<grid_a, 32 * kK3aWarps, smem_a, st>>>(P, maxpx, (uint32_t)t0, nl, slot.ptr);
-        else k3a_front_kernel<false><<<grid_a, 32 * kK3aWarps, smem_a, st>>>(P, maxpx, (uint32_t)t0, nl, slot.ptr);
+        const int pf = bps_a * kK3aWarps < 16;              // few warps per SM (large strides): pull the next tile into L2
+        if (masked) k3a_front_kernel<true><<<grid_a, 32 * kK3aWarps, smem_a, st>>>(P, maxpx, (uint32_t)t0, nl, slot.ptr, pf);
+        else k3a_front_kernel<false><<<grid_a, 32 * kK3aWarps, smem_a, st>>>(P, maxpx, (uint32_t)t0, nl, slot.ptr, pf);
         const long long res_b = (long long)ctx->sm_count * bps_b;
         const int grid_b = (int)(nl < res_b ? nl : res_b);
         if (masked) k3_glcm_kernel<true, DUMP, NT, TB><<<grid_b, NT, smem_b, st>>>(P, maxpx, nl, slot.ptr);

@@ -441,7 +441,7 @@ __device__ __noinline__ void k3_slow_direction(K3Smem& S, const uint32_t* hist, 
 template <bool MASKED>
 __global__ void __launch_bounds__(32 * kK3aWarps)
 k3a_front_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t tile_base, uint32_t n_local,
-                 unsigned char* __restrict__ scratch) {
+                 unsigned char* __restrict__ scratch, int prefetch) {
     extern __shared__ __align__(16) unsigned char k3a_smem_raw[];
     __shared__ double homtab[256];
     constexpr int NG = MASKED ? 2 : 4;           // groups of 4 pairs per item
@@ -465,13 +465,15 @@ k3a_front_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t tile
         return __ldg(P.out + (long long)row * P.row_stride + P.col_basic + kNBasic * (int)slot + 10);
     };
 
-    long long tnext = next_tile(P.sched + 5);
+    long long tnext = next_tile(P.sched + 5), tnext2 = next_tile(P.sched + 5);
     double vnext = k1_max_of(tnext);
     while (tnext < (long long)n_local) {
         const uint32_t tl = (uint32_t)tnext;
         const double vmaxd = vnext;
-        tnext = next_tile(P.sched + 5);                       // one tile ahead
+        tnext = tnext2;
+        tnext2 = next_tile(P.sched + 5);                      // two tiles ahead: the next one is known now ...
         vnext = k1_max_of(tnext);
+        if (prefetch) prefetch_tile_l2(P, (long long)tile_base + tnext, (long long)tile_base + n_local);   // ... and on its way into L2
         const Tile T = resolve_tile(P, (long long)(tile_base + tl));
         const int tw = T.w, th = T.h, tn = T.n;
         const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
