@@ -642,3 +642,46 @@ def test_k1_fourth_power_sum_beyond_64_bits(torch_mod):
     img = np.stack([b.astype(np.uint16) for b in small], axis=2)[None]
     cols = imf.feature_columns(img.shape[3])
     compare_tables(imf.extract_features(img), c_oracle.table(_planar(img)), cols, label="k1 s4 bimodal")
+
+
+def test_round2_paths_edge_cases(torch_mod):
+    """The code paths added late in round 2, on inputs chosen to hit their corners:
+    * K4w's general vector pass: row lengths 8..15 and other non-multiples of 8 (chunks that straddle row ends, a
+      partial last chunk), next to row lengths below 8 (scalar pass) in the same size-table batch;
+    * K3's bounding-box records: masks confined to the last rows / first rows / one row / one column / one pixel,
+      a full mask and an empty one;
+    * K2's two-level percentile search: full-16-bit data with duplicates, masked, with percentiles from 0 to 100."""
+    rng = np.random.default_rng(77)
+    shapes = [(9, 8), (11, 9), (16, 15), (5, 13), (64, 10), (7, 5), (3, 3), (33, 71), (128, 12), (12, 128), (31, 100), (64, 64)]
+    C = 3
+    objs, masks = [], []
+    for k, (h, w) in enumerate(shapes):
+        o = rng.integers(0, 65536, (h, w, C)).astype(np.uint16)
+        o[:, :, 1] = rng.integers(0, 7, (h, w)) * 9000                  # wide range, heavy duplicates
+        o[:, :, 2] = rng.integers(100, 3000, (h, w))                    # 12-bit plane
+        m = np.zeros((h, w, C), np.uint8)
+        kind = k % 6
+        if kind == 0: m[h - 2:, :, :] = 1                               # last rows
+        elif kind == 1: m[:1, :, :] = 1                                 # one row
+        elif kind == 2: m[:, w - 1:, :] = 1                             # one column (no horizontal pair)
+        elif kind == 3: m[h // 2, w // 2, :] = 1                        # one pixel
+        elif kind == 4: m[:, :, :] = 1                                  # full
+        else: m[:, :, 0] = (rng.random((h, w)) < 0.5); m[:, :, 1] = 0; m[:, :, 2] = (rng.random((h, w)) < 0.1)   # channel 1: empty
+        objs.append(o)
+        masks.append(m)
+    qs = (0.0, 0.5, 5.0, 25.0, 50.0, 75.0, 95.0, 99.5, 100.0)
+    cols = imf.feature_columns(C, n_angles=4, shape=True, moments=True)
+    for use_mask in (True, False):
+        got = imf.extract_features(objs, masks if use_mask else None, four_directions=True, shape=True, moments=True,
+                                   percentiles=qs)
+        for i, (o, m) in enumerate(zip(objs, masks)):
+            want = c_oracle.table(_planar(o[None]), _planar(m[None]) if use_mask else None, glcm=True, n_angles=4,
+                                  shape=True, moments=True)
+            # the oracle's percentile columns are the notebook's literals: take np.percentile for the custom ones
+            for c in range(C):
+                sel = o[:, :, c][m[:, :, c] > 0] if use_mask else o[:, :, c].ravel()
+                for j, q in enumerate(qs):
+                    col = cols.index("percentile%d0_intensity_Ch%d" % (j + 1, c + 1))
+                    want[0, col] = np.percentile(sel, q) if sel.size else np.nan
+            compare_tables(got[i:i + 1], want, cols, label="r2 edge %d %s mask=%s" % (i, o.shape[:2], use_mask),
+                           images=[o], masks=[m] if use_mask else None)
