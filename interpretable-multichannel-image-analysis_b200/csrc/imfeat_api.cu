@@ -63,7 +63,7 @@ struct imfeat_ctx {
     cudaEvent_t t_side[kTimingSlots][2];   // K4 on the side stream (overlap mode): its own start / end
     // overlap mode: K4w runs on a side stream next to K3 (its few resident warps fill the issue slots the
     // shared-memory-bound GLCM kernels leave free)
-    int env_overlap, env_k4_fill;
+    int env_overlap, env_k4_fill, env_k3_tiers;
     cudaStream_t side[4];
     cudaEvent_t fork_ev[8], join_ev[8];
     unsigned int side_head;
@@ -168,6 +168,7 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
         ctx->env_overlap = flag("IMFEAT_OVERLAP", 0);       // 1: K4w on a side stream next to K3, 2: next to K12 as well (measured: no gain); 0: one stream
         ctx->env_k4_fill = flag("IMFEAT_K4_FILL", 4);       // resident K4w warps per SM while it runs next to K3
         if (ctx->env_k4_fill < 1) ctx->env_k4_fill = 1;
+        ctx->env_k3_tiers = flag("IMFEAT_K3_TIERS", 1);     // 0: K3 with room for a whole tile only (no first tier for large strides)
     }
     ctx->sm_count = prop.multiProcessorCount;
     // log2 table, computed on the host in double precision (k = 0 maps to 0, never used)
@@ -307,16 +308,38 @@ static int grow_buffer(imfeat_ctx* ctx, cudaStream_t st, void** buf, size_t byte
 // scratch records of a chunk are still in L2 when the bins kernel fetches them.
 template <bool DUMP, int NT, int TB>
 static int launch_k3_nt(imfeat_ctx* ctx, bool masked, cudaStream_t st, const Params& P, int maxpx) {
-    const size_t rec = k3_rec_bytes(maxpx, masked);
-    const size_t smem_b = k3_smem_bytes(maxpx, masked, TB), smem_a = (size_t)kK3aWarps * k3a_warp_bytes(maxpx, masked);
-    int bps_a = 0, bps_b = 0;
-    cudaError_t e = masked ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_b, k3_glcm_kernel<true, DUMP, NT, TB>, NT, smem_b)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_b, k3_glcm_kernel<false, DUMP, NT, TB>, NT, smem_b);
-    if (e == cudaSuccess)
-        e = masked ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_a, k3a_front_kernel<true>, 32 * kK3aWarps, smem_a)
-                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_a, k3a_front_kernel<false>, 32 * kK3aWarps, smem_a);
-    if (e != cudaSuccess) return fail(ctx, IMFEAT_ERR_CUDA, "K3 occupancy query failed: %s", cudaGetErrorString(e));
-    if (bps_a < 1 || bps_b < 1) return fail(ctx, IMFEAT_ERR_CUDA, "K3 does not fit an SM (%zu / %zu bytes of shared memory)", smem_a, smem_b);
+    // Capacity per tile.  Large strides with masks: two tiers (see K3Cap) -- the first holds the rows of a sparse
+    // mask's bounding box and runs three times as many warps / CTAs per SM; the tiles it leaves over are listed
+    // and taken by a second pair of launches with room for a whole tile.
+    const int mb_px = ((P.hs * P.ws + 7) & ~7);
+    const K3Cap cap_full = {maxpx, mb_px};
+    int q1 = maxpx;
+    if (masked && !DUMP && maxpx > 8192 && ctx->env_k3_tiers) {
+        q1 = (maxpx / 3 + 15) & ~15;
+        if (q1 < 4352) q1 = 4352;
+    }
+    const bool two = q1 < maxpx;
+    const K3Cap cap1 = {q1, mb_px};
+    struct Shape { size_t rec, smem_a, smem_b; int bps_a, bps_b; };
+    auto shape_of = [&](K3Cap cap, Shape& sh) -> int {
+        sh.rec = k3_rec_bytes(cap, masked);
+        sh.smem_b = k3_smem_bytes(cap, masked, TB);
+        sh.smem_a = (size_t)kK3aWarps * k3a_warp_bytes(cap, masked);
+        sh.bps_a = sh.bps_b = 0;
+        cudaError_t e = masked ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sh.bps_b, k3_glcm_kernel<true, DUMP, NT, TB>, NT, sh.smem_b)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sh.bps_b, k3_glcm_kernel<false, DUMP, NT, TB>, NT, sh.smem_b);
+        if (e == cudaSuccess)
+            e = masked ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sh.bps_a, k3a_front_kernel<true>, 32 * kK3aWarps, sh.smem_a)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sh.bps_a, k3a_front_kernel<false>, 32 * kK3aWarps, sh.smem_a);
+        if (e != cudaSuccess) return fail(ctx, IMFEAT_ERR_CUDA, "K3 occupancy query failed: %s", cudaGetErrorString(e));
+        if (sh.bps_a < 1 || sh.bps_b < 1)
+            return fail(ctx, IMFEAT_ERR_CUDA, "K3 does not fit an SM (%zu / %zu bytes of shared memory)", sh.smem_a, sh.smem_b);
+        return IMFEAT_OK;
+    };
+    Shape s1, s2;
+    int rcs = shape_of(cap1, s1);
+    if (rcs) return rcs;
+    if (two) { rcs = shape_of(cap_full, s2); if (rcs) return rcs; }
     // chunks of whole objects, evenly sized
     const long long chunk_tiles = (long long)ctx->env_k3_chunk * P.c_out;
     const long long n_chunks = (P.n_tiles + chunk_tiles - 1) / chunk_tiles;
@@ -326,27 +349,50 @@ static int launch_k3_nt(imfeat_ctx* ctx, bool masked, cudaStream_t st, const Par
     CU(cudaStreamIsCapturing(st, &cap));
     auto& slot = ctx->scr[ctx->scr_head++ & 1u];
     if (cap == cudaStreamCaptureStatusNone && slot.recorded) CU(cudaStreamWaitEvent(st, slot.ev, 0));
-    const size_t scr_bytes = (size_t)per * (rec + sizeof(uint32_t));       // the records, then the table of their lengths
+    // layout: first-tier records, their lengths | the list of left-over tiles | second-tier records, their lengths
+    const size_t off_wl = (((size_t)per * (s1.rec + sizeof(uint32_t))) + 255) & ~(size_t)255;
+    const size_t off_r2 = two ? ((off_wl + (size_t)per * sizeof(uint32_t) + 255) & ~(size_t)255) : off_wl;
+    const size_t scr_bytes = two ? off_r2 + (size_t)per * (s2.rec + sizeof(uint32_t)) : off_wl;
     if (slot.bytes < scr_bytes) {
         if (cap == cudaStreamCaptureStatusNone && slot.recorded) CU(cudaEventSynchronize(slot.ev));
         int rc = grow_buffer(ctx, st, (void**)&slot.ptr, scr_bytes, "K3 scratch");
         if (rc) { slot.bytes = 0; return rc; }
         slot.bytes = scr_bytes;
     }
+    // work counters of one round (slots of the call's counter set): front / bins of tier 1, of tier 2, left-over count
+    unsigned int* const c_a1 = P.sched + 5; unsigned int* const c_b1 = P.sched + 6;
+    unsigned int* const c_a2 = P.sched + 2; unsigned int* const c_b2 = P.sched + 4; unsigned int* const c_left = P.sched + 7;
+    auto launch_pair = [&](const Shape& sh, K3Cap cp, long long t0, uint32_t nl, unsigned char* scr, const K3Tier& ta, const K3Tier& tb) {
+        const long long warps_a = (long long)ctx->sm_count * sh.bps_a * kK3aWarps;
+        const int grid_a = (int)((nl < warps_a ? nl : warps_a) + kK3aWarps - 1) / kK3aWarps;
+        const int pf = sh.bps_a * kK3aWarps < 16;           // few warps per SM (large strides): pull the next tile into L2
+        if (masked) k3a_front_kernel<true><<<grid_a, 32 * kK3aWarps, sh.smem_a, st>>>(P, cp, (uint32_t)t0, nl, scr, pf, ta);
+        else k3a_front_kernel<false><<<grid_a, 32 * kK3aWarps, sh.smem_a, st>>>(P, cp, (uint32_t)t0, nl, scr, pf, ta);
+        const long long res_b = (long long)ctx->sm_count * sh.bps_b;
+        const int grid_b = (int)(nl < res_b ? nl : res_b);
+        if (masked) k3_glcm_kernel<true, DUMP, NT, TB><<<grid_b, NT, sh.smem_b, st>>>(P, cp, nl, scr, tb);
+        else k3_glcm_kernel<false, DUMP, NT, TB><<<grid_b, NT, sh.smem_b, st>>>(P, cp, nl, scr, tb);
+        ctx->launches += 2;
+    };
     for (long long c = 0; c < n_chunks; ++c) {
         const long long t0 = c * per;
         const uint32_t nl = (uint32_t)(P.n_tiles - t0 < per ? P.n_tiles - t0 : per);
         CU(cudaMemsetAsync(P.sched + 5, 0, 2 * sizeof(unsigned int), st));     // the tile counters of the two kernels
-        const long long warps_a = (long long)ctx->sm_count * bps_a * kK3aWarps;
-        const int grid_a = (int)((nl < warps_a ? nl : warps_a) + kK3aWarps - 1) / kK3aWarps;
-        const int pf = bps_a * kK3aWarps < 16;              // few warps per SM (large strides): pull the next tile into L2
-        if (masked) k3a_front_kernel<true><<<grid_a, 32 * kK3aWarps, smem_a, st>>>(P, maxpx, (uint32_t)t0, nl, slot.ptr, pf);
-        else k3a_front_kernel<false><<<grid_a, 32 * kK3aWarps, smem_a, st>>>(P, maxpx, (uint32_t)t0, nl, slot.ptr, pf);
-        const long long res_b = (long long)ctx->sm_count * bps_b;
-        const int grid_b = (int)(nl < res_b ? nl : res_b);
-        if (masked) k3_glcm_kernel<true, DUMP, NT, TB><<<grid_b, NT, smem_b, st>>>(P, maxpx, nl, slot.ptr);
-        else k3_glcm_kernel<false, DUMP, NT, TB><<<grid_b, NT, smem_b, st>>>(P, maxpx, nl, slot.ptr);
-        ctx->launches += 2;
+        uint32_t* wl = reinterpret_cast<uint32_t*>(slot.ptr + off_wl);
+        if (two) {
+            CU(cudaMemsetAsync(c_a2, 0, sizeof(unsigned int), st));
+            CU(cudaMemsetAsync(c_b2, 0, sizeof(unsigned int), st));
+            CU(cudaMemsetAsync(c_left, 0, sizeof(unsigned int), st));
+        }
+        const K3Tier ta1 = {nullptr, nullptr, two ? wl : nullptr, two ? c_left : nullptr, c_a1};
+        const K3Tier tb1 = {nullptr, nullptr, nullptr, nullptr, c_b1};
+        launch_pair(s1, cap1, t0, nl, slot.ptr, ta1, tb1);
+        if (two) {
+            // the tiles the first tier listed (their number is known on the device only: the grids are sized for all)
+            const K3Tier ta2 = {wl, c_left, nullptr, nullptr, c_a2};
+            const K3Tier tb2 = {wl, c_left, nullptr, nullptr, c_b2};
+            launch_pair(s2, cap_full, t0, nl, slot.ptr + off_r2, ta2, tb2);
+        }
     }
     const long long recs = P.n_tiles * P.n_angles;
     const long long want = (recs + 255) / 256, capg = 8ll * ctx->sm_count;

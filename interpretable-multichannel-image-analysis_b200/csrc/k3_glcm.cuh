@@ -38,6 +38,19 @@ constexpr int kK3MaxWarps = 8;
 // item reads) and mask bits (masked variant only)
 __host__ __device__ inline int k3_q8_words(int max_pixels) { return (max_pixels / 4 + 8 + 3) & ~3; }
 __host__ __device__ inline int k3_mb_words(int max_pixels, bool masked) { return masked ? ((max_pixels / 32 + 2 + 3) & ~3) : 0; }
+// What a launch of the two kernels can hold per tile: q8 bytes of quantised rows, mask bits for mb pixels.  A batch
+// of large strides is worked off in two tiers: first with room for about a third of a full tile's rows -- enough
+// for the bounding box of a sparse mask, and three times as many warps / CTAs per SM --, then the tiles whose
+// box did not fit (the front kernel lists them) with room for everything.
+struct K3Cap { int q8, mb; };
+struct K3Tier {
+    const uint32_t* wl_in;       // tiles of this launch (second tier), or NULL: tile_base + 0 .. n_local - 1
+    const uint32_t* n_in;        // their number (device), with wl_in
+    uint32_t* wl_out;            // first tier: where tiles that do not fit are listed (NULL: every tile fits)
+    uint32_t* n_out;
+    unsigned int* counter;       // the launch's dynamic tile counter
+};
+constexpr uint32_t kK3Skip = 16u;      // record length of a tile left to the second tier (a real record is longer)
 
 // An item is a run of up to 4*NG horizontally consecutive pairs (NG groups of 4) of one row: the words
 // of both pixel runs are loaded once and funnel-shifted into place.  Unmasked tiles use 16-pair items;
@@ -64,8 +77,8 @@ struct alignas(16) K3Hdr {
     uint32_t tile, len;                            // len: bytes of this record that are in use (multiple of 16)
 };
 static_assert(sizeof(K3Hdr) == 272, "multiple of 16 bytes");
-__host__ __device__ inline size_t k3_rec_bytes(int max_pixels, bool masked) {
-    return sizeof(K3Hdr) + 4 * (size_t)(k3_q8_words(max_pixels) + k3_mb_words(max_pixels, masked));
+__host__ __device__ inline size_t k3_rec_bytes(K3Cap cap, bool masked) {
+    return sizeof(K3Hdr) + 4 * (size_t)(k3_q8_words(cap.q8) + k3_mb_words(cap.mb, masked));
 }
 
 struct alignas(16) K3Smem {                     // behind the table (64 or 32 KB), before the two record buffers
@@ -79,13 +92,13 @@ struct K3Group {                               // where the quantised tile and i
     uint32_t* q8;                              // quantised pixels (bytes) + slack for unaligned reads
     uint32_t* mbits;                           // one bit per pixel: inside the mask (masked variant)
 };
-__host__ __device__ inline size_t k3_smem_bytes(int max_pixels, bool masked, int table_kb) {
+__host__ __device__ inline size_t k3_smem_bytes(K3Cap max_pixels, bool masked, int table_kb) {
     // two record buffers: the next tile lands while this one is worked off
     return (size_t)table_kb * 1024 + sizeof(K3Smem) + 2 * k3_rec_bytes(max_pixels, masked);
 }
 // front kernel: per warp one record being assembled + the four output records
 constexpr int kK3aWarps = 4;                    // warps per CTA of the front kernel
-__host__ __device__ inline size_t k3a_warp_bytes(int max_pixels, bool masked) {
+__host__ __device__ inline size_t k3a_warp_bytes(K3Cap max_pixels, bool masked) {
     return k3_rec_bytes(max_pixels, masked) + 16 * ((kMaxAngles * kK3Rec * 4 + 15) / 16);
 }
 
@@ -440,41 +453,46 @@ __device__ __noinline__ void k3_slow_direction(K3Smem& S, const uint32_t* hist, 
 // scratch record of the tile for the bins kernel.
 template <bool MASKED>
 __global__ void __launch_bounds__(32 * kK3aWarps)
-k3a_front_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t tile_base, uint32_t n_local,
-                 unsigned char* __restrict__ scratch, int prefetch) {
+k3a_front_kernel(const __grid_constant__ Params P, K3Cap max_pixels, uint32_t tile_base, uint32_t n_local_host,
+                 unsigned char* __restrict__ scratch, int prefetch, K3Tier tier) {
     extern __shared__ __align__(16) unsigned char k3a_smem_raw[];
     __shared__ double homtab[256];
     constexpr int NG = MASKED ? 2 : 4;           // groups of 4 pairs per item
     constexpr int NP = 4 * NG;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_local = tier.wl_in ? min(*tier.n_in, n_local_host) : n_local_host;
     const size_t rec_bytes = k3_rec_bytes(max_pixels, MASKED);
     unsigned char* mine = k3a_smem_raw + (size_t)warp * k3a_warp_bytes(max_pixels, MASKED);
     K3Hdr& H = *reinterpret_cast<K3Hdr*>(mine);
     K3Group Gp;
     Gp.mbits = reinterpret_cast<uint32_t*>(mine + sizeof(K3Hdr));
-    Gp.q8 = Gp.mbits + k3_mb_words(max_pixels, MASKED);
+    Gp.q8 = Gp.mbits + k3_mb_words(max_pixels.mb, MASKED);
     uint32_t* recs = reinterpret_cast<uint32_t*>(mine + rec_bytes);      // [n_angles][kK3Rec]
-    uint32_t* const rec_len = reinterpret_cast<uint32_t*>(scratch + (size_t)n_local * rec_bytes);
+    uint32_t* const rec_len = reinterpret_cast<uint32_t*>(scratch + (size_t)n_local_host * rec_bytes);
+    auto tile_of = [&](long long tl) -> long long {          // global tile index of local tile tl
+        return tier.wl_in ? (long long)tier.wl_in[tl] : (long long)tile_base + tl;
+    };
     for (int k = threadIdx.x; k < 256; k += blockDim.x) homtab[k] = 1.0 / (1.0 + (double)(k * k));
     __syncthreads();
     const bool k1_max = P.col_basic >= 0;
     auto k1_max_of = [&](long long tl) -> double {            // K1 (earlier launch, same stream) left the maximum in the table
         if (!k1_max || tl >= (long long)n_local) return 0.0;
-        const uint32_t tile = tile_base + (uint32_t)tl;
+        const uint32_t tile = (uint32_t)tile_of(tl);
         const uint32_t row = tile / (uint32_t)P.c_out, slot = tile - row * (uint32_t)P.c_out;
         return __ldg(P.out + (long long)row * P.row_stride + P.col_basic + kNBasic * (int)slot + 10);
     };
 
-    long long tnext = next_tile(P.sched + 5), tnext2 = next_tile(P.sched + 5);
+    long long tnext = next_tile(tier.counter), tnext2 = next_tile(tier.counter);
     double vnext = k1_max_of(tnext);
     while (tnext < (long long)n_local) {
         const uint32_t tl = (uint32_t)tnext;
         const double vmaxd = vnext;
         tnext = tnext2;
-        tnext2 = next_tile(P.sched + 5);                      // two tiles ahead: the next one is known now ...
+        tnext2 = next_tile(tier.counter);                      // two tiles ahead: the next one is known now ...
         vnext = k1_max_of(tnext);
-        if (prefetch) prefetch_tile_l2(P, (long long)tile_base + tnext, (long long)tile_base + n_local);   // ... and on its way into L2
-        const Tile T = resolve_tile(P, (long long)(tile_base + tl));
+        if (prefetch && tnext < (long long)n_local) prefetch_tile_l2(P, tile_of(tnext), P.n_tiles);   // ... and on its way into L2
+        const long long tile_id = tile_of(tl);
+        const Tile T = resolve_tile(P, tile_id);
         const int tw = T.w, th = T.h, tn = T.n;
         const uint4* px4 = reinterpret_cast<const uint4*>(T.px);
         const uint2* mk2 = reinterpret_cast<const uint2*>(T.mk);
@@ -561,6 +579,15 @@ k3a_front_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t tile
         const int i0 = p_lo >> 3, i1 = min(nfull, (p_hi + 7) >> 3);
         const int qbias = pitch == tw ? (p_lo & ~7) : brmin * pitch;
         const uint32_t q8_used = (uint32_t)((pitch == tw ? p_hi : (brmax + 1) * pitch) - qbias);
+        if (tier.wl_out && q8_used > (uint32_t)max_pixels.q8) {
+            // the rows of this mask's bounding box do not fit this tier: leave the tile to the next one
+            if (lane == 0) {
+                tier.wl_out[atomicAdd(tier.n_out, 1u)] = (uint32_t)tile_id;
+                rec_len[tl] = kK3Skip;
+            }
+            __syncwarp();
+            continue;
+        }
         const float rcpr = __frcp_rn((float)max(cpr, 1));
         auto quant_chunk = [&](int idx, const uint4& v) {              // out-of-mask pixels may exceed the maximum:
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};               // their bytes are never part of a pair
@@ -602,10 +629,10 @@ k3a_front_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t tile
         }
         // geometry of the directions: lane a works out direction a
         if (lane < P.n_angles) H.geom[lane] = k3_geom<MASKED, NG>(tw, P.dr[lane], P.dc[lane], brmin, brmax, bcmin, bcmax, qbias);
-        const uint32_t len = ((uint32_t)sizeof(K3Hdr) + 4u * (uint32_t)k3_mb_words(max_pixels, MASKED) + q8_used + 15u) & ~15u;
+        const uint32_t len = ((uint32_t)sizeof(K3Hdr) + 4u * (uint32_t)k3_mb_words(max_pixels.mb, MASKED) + q8_used + 15u) & ~15u;
         if (lane == 0) {
             H.rec = reinterpret_cast<uint32_t*>(T.out_row + P.col_glcm + T.slot * P.n_angles * kNGlcm);
-            H.tile = tile_base + tl; H.len = len;
+            H.tile = (uint32_t)tile_id; H.len = len;
             rec_len[tl] = len;
         }
         __syncwarp();
@@ -662,7 +689,8 @@ k3a_front_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t tile
 // a wrap starts the next directions with the 8-bit halves at once.
 template <bool MASKED, bool DUMP, int NT, int TB>
 __global__ void __launch_bounds__(NT, TB == 64 ? 3 : 5)
-k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t n_local, const unsigned char* __restrict__ scratch) {
+k3_glcm_kernel(const __grid_constant__ Params P, K3Cap max_pixels, uint32_t n_local_host, const unsigned char* __restrict__ scratch,
+               K3Tier tier) {
     extern __shared__ __align__(16) unsigned char k3_smem_raw[];
     uint32_t* const hist = reinterpret_cast<uint32_t*>(k3_smem_raw);
     K3Smem& S = *reinterpret_cast<K3Smem*>(k3_smem_raw + TB * 1024);
@@ -673,17 +701,19 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t n_loca
     constexpr int NW = NT / 32;
     static_assert(NW <= kK3MaxWarps && KC >= 1, "CTA size");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_local = tier.wl_in ? min(*tier.n_in, n_local_host) : n_local_host;
+    if (blockIdx.x >= n_local) return;
     const uint32_t rec_bytes = (uint32_t)k3_rec_bytes(max_pixels, MASKED);
     unsigned char* recbuf0 = k3_smem_raw + TB * 1024 + sizeof(K3Smem);
     const uint32_t hist_addr = smem_addr(hist), bar0 = smem_addr(&S.mbar[0]), rec_addr0 = smem_addr(recbuf0);
-    const uint32_t* const rec_len = reinterpret_cast<const uint32_t*>(scratch + (size_t)n_local * rec_bytes);
+    const uint32_t* const rec_len = reinterpret_cast<const uint32_t*>(scratch + (size_t)n_local_host * rec_bytes);
 
     for (int k = tid; k < TB * 256; k += NT) hist[k] = 0u;
     if (tid == 0) {
         // tiles: the first one is the CTA's own index, the others come from the per-launch counter (so the
         // tail does not depend on how many CTAs are resident at once), drawn two tiles ahead
         S.tq[0] = blockIdx.x;
-        S.tq[1] = gridDim.x + atomicAdd(P.sched + 6, 1u);
+        S.tq[1] = gridDim.x + atomicAdd(tier.counter, 1u);
         S.tlen[0] = blockIdx.x < n_local ? rec_len[blockIdx.x] : 0u;
         S.tlen[1] = S.tq[1] < n_local ? rec_len[S.tq[1]] : 0u;
         S.slow[0] = 0u; S.slow[1] = 0u; S.slow[2] = 0u;
@@ -709,7 +739,7 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t n_loca
         const uint32_t b = j & 1u;
         uint32_t t_draw = 0u, len_draw = 0u;
         if (tid == 0) {
-            t_draw = gridDim.x + atomicAdd(P.sched + 6, 1u);
+            t_draw = gridDim.x + atomicAdd(tier.counter, 1u);
             const uint32_t t_next = S.tq[(j + 1) & 3u];
             if (t_next < n_local) fetch(t_next, b ^ 1u, S.tlen[(j + 1) & 3u]);     // that buffer's tile (j - 1) was finished before the last barrier
             if (t_draw < n_local) len_draw = rec_len[t_draw];
@@ -717,8 +747,13 @@ k3_glcm_kernel(const __grid_constant__ Params P, int max_pixels, uint32_t n_loca
         const K3Hdr& H = *reinterpret_cast<const K3Hdr*>(recbuf0 + b * rec_bytes);
         K3Group Gp;
         Gp.mbits = reinterpret_cast<uint32_t*>(recbuf0 + b * rec_bytes + sizeof(K3Hdr));
-        Gp.q8 = Gp.mbits + k3_mb_words(max_pixels, MASKED);
+        Gp.q8 = Gp.mbits + k3_mb_words(max_pixels.mb, MASKED);
         mbar_wait(bar0 + 8 * b, (j >> 1) & 1u);            // ---- record landed ----
+        if (S.tlen[j & 3u] == kK3Skip) {                   // a tile left to the second tier: nothing to do here
+            if (tid == 0) { S.tq[(j + 2) & 3u] = t_draw; S.tlen[(j + 2) & 3u] = len_draw; }
+            __syncthreads();
+            continue;
+        }
 
 #pragma unroll 1
         for (int a = 0; a < P.n_angles; ++a, ++dcount) {
