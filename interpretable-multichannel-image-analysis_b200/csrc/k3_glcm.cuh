@@ -451,8 +451,11 @@ __device__ __noinline__ void k3_slow_direction(K3Smem& S, const uint32_t* hist, 
 // the mask bits and their bounding box, works out the geometry of every direction, adds up the pair-stream
 // sums of every direction into the output records, and leaves header + quantised pixels + mask bits in the
 // scratch record of the tile for the bins kernel.
+#ifndef IMFEAT_K3A_CTAS
+#define IMFEAT_K3A_CTAS 8               // resident CTAs per SM the register budget is set for
+#endif
 template <bool MASKED>
-__global__ void __launch_bounds__(32 * kK3aWarps)
+__global__ void __launch_bounds__(32 * kK3aWarps, IMFEAT_K3A_CTAS)
 k3a_front_kernel(const __grid_constant__ Params P, K3Cap max_pixels, uint32_t tile_base, uint32_t n_local_host,
                  unsigned char* __restrict__ scratch, int prefetch, K3Tier tier) {
     extern __shared__ __align__(16) unsigned char k3a_smem_raw[];
