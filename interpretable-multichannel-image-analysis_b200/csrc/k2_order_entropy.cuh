@@ -217,6 +217,8 @@ __global__ void __launch_bounds__(1024, 1) k2_order_entropy_kernel(const __grid_
     extern __shared__ __align__(16) unsigned char k2_smem_raw[];
     K2Smem& S = *reinterpret_cast<K2Smem*>(k2_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
+    // nothing on the worklist for this CTA (12-bit data: nothing at all): leave before the 160 KB of tables are set up
+    if (worklist && (long long)blockIdx.x >= (long long)*worklist_count) return;
     Ring R;
     ring_init(R, S.tokens, ng);
     const int g = R.g, gt = R.gt, gw = R.gw, gthreads = R.gthreads;
