@@ -42,6 +42,9 @@ __device__ __forceinline__ void k12_px(K2cSmem& S, uint32_t x, uint32_t inb, uin
 // the eight pixels of one 128-bit load: K1's exact integer sums, and (HIST) one histogram add per pixel
 template <bool MASKED, bool HIST>
 __device__ __forceinline__ void k12_vec(K2cSmem& S, const uint4& v, const uint2& m, int p, uint32_t base, K1IntState& st) {
+    // eight pixels outside the mask add nothing to any sum, to the extrema or to the histogram: skip them.  Rows
+    // above and below a mask's bounding box are whole warp iterations (32 lanes x 8 pixels = 4 rows of 64).
+    if (MASKED && (m.x | m.y) == 0u) return;
     uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t h[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
     uint32_t nz[2] = {0xffffffffu, 0xffffffffu};

@@ -442,6 +442,10 @@ __global__ void __launch_bounds__(32, IMFEAT_K4W_WARPS) k4w_shape_kernel(const _
             unsigned long long B10 = 0, B20 = 0, B30 = 0, B11 = 0, B21 = 0, B12 = 0;
             auto chunk = [&](int r, uint4 v, uint2 m) {
                 uint32_t bits8 = 0xffu, b03 = 0x01010101u, b47 = 0x01010101u;
+                if (MASKED && (m.x | m.y) == 0u) {          // nothing of the mask here: only its (zero) bits are recorded
+                    mbytes[r * (Pw << 2)] = (uint8_t)0;
+                    return;
+                }
                 if (MASKED) {
                     const uint32_t n0 = __vcmpne4(m.x, 0u), n1 = __vcmpne4(m.y, 0u);
                     b03 = n0 & 0x01010101u; b47 = n1 & 0x01010101u;
@@ -548,6 +552,7 @@ __global__ void __launch_bounds__(32, IMFEAT_K4W_WARPS) k4w_shape_kernel(const _
                 }
             };
             auto chunk = [&](int idx, const uint4& v, const uint2& m) {
+                if (MASKED && (m.x | m.y) == 0u) return;   // nothing of the mask here (its row words are zero already)
                 const int p0 = idx << 3;
                 const int r = (int)(((float)p0 + 0.5f) * rtw), c = p0 - r * w;          // exact: p0 < 2^20
                 const int nv = min(8, n - p0), na = min(nv, w - c);                    // pixels of the chunk; of them in row r
