@@ -630,8 +630,9 @@ __global__ void __launch_bounds__(32, IMFEAT_K4W_WARPS) k4w_shape_kernel(const _
         __syncwarp();
         // ---- pass B: border = mask & ~erosion4(mask), 32 pixels per word ----
         const int words = h * Pw;
+        const float rPw = __frcp_rn((float)Pw);
         for (int idx = lane; idx < words; idx += 32) {
-            const int r = idx / Pw, cw = idx - r * Pw;
+            const int r = (int)(((float)idx + 0.5f) * rPw), cw = idx - r * Pw;   // exact: idx < 2^20
             const uint32_t m = mrow[idx];
             const uint32_t up = r > 0 ? mrow[idx - Pw] : 0u, dn = r + 1 < h ? mrow[idx + Pw] : 0u;
             const uint32_t ml = cw > 0 ? mrow[idx - 1] : 0u, mr2 = cw + 1 < Pw ? mrow[idx + 1] : 0u;
@@ -644,7 +645,7 @@ __global__ void __launch_bounds__(32, IMFEAT_K4W_WARPS) k4w_shape_kernel(const _
         for (int idx = lane; idx < words; idx += 32) {
             const uint32_t b = brow[idx];
             if (!b) continue;
-            const int r = idx / Pw, cw = idx - r * Pw;
+            const int r = (int)(((float)idx + 0.5f) * rPw), cw = idx - r * Pw;   // exact: idx < 2^20
             const bool hu = r > 0, hd = r + 1 < h, hl = cw > 0, hr = cw + 1 < Pw;
             const uint32_t bl = hl ? brow[idx - 1] : 0u, br = hr ? brow[idx + 1] : 0u;
             const uint32_t u = hu ? brow[idx - Pw] : 0u, ul = (hu && hl) ? brow[idx - Pw - 1] : 0u;
