@@ -431,8 +431,8 @@ def run_b200(args):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "traffic_source": tsrc, "algorithmic_bytes": b_path,
                      "note": "SURVEY 8(d): algorithmic bytes = N*(2hwC + 1*hwC + 8*60*C), counted ONCE for the whole step however often a kernel re-reads the tile; "
-                             "divided by the CUDA-event time of the step.  ncu: K3's two kernels run at 70-75% of the shared-memory pipe (their roofline), "
-                             "K12 / K4 at 60-68% instruction issue; none is HBM-bound (profiles/)"},
+                             "divided by the CUDA-event time of the step.  ncu: K3's two kernels run at 77-82% of the shared-memory pipe (their roofline), "
+                             "K12 / K4 at 62-64% instruction issue; none is HBM-bound (profiles/)"},
         "roofline_kernels": per_kernel,
         "roofline_basic_block": {"ms_per_step": basic_ms, "frac": b_basic / (basic_ms * 1e-3) / 1e9 / peak if basic_ms else None,
                                  "note": "the 17 intensity/percentile/entropy columns: N*(2hwC + hwC + 8*17*C) bytes over the time of K12 + the full-range worklist kernel"},
