@@ -3,6 +3,22 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Device-side bounds checks (-DIMFEAT_CHECKS, profiles/build_variant.sh): every shared-memory table, staging buffer
+// and work-list index the kernels compute is tested and a violation traps the kernel -- the GPU test-suite run on
+// such a build stands in for compute-sanitizer's memcheck, which is closed on this GPU pool (profiles/).
+#ifdef IMFEAT_CHECKS
+#include <stdio.h>
+#define IMFEAT_CHECK(cond)                                                                   \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            printf("IMFEAT_CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__);           \
+            __trap();                                                                        \
+        }                                                                                    \
+    } while (0)
+#else
+#define IMFEAT_CHECK(cond) ((void)0)
+#endif
+
 namespace imfeat {
 
 constexpr int kNBasic = 17;

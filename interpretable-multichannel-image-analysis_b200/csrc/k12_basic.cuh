@@ -36,6 +36,10 @@ __device__ __forceinline__ void k12_px(K2cSmem& S, uint32_t x, uint32_t inb, uin
     uint32_t off = (bin << 1) & (uint32_t)(kK2cWords * 4 - 4);
     const uint32_t inc = __funnelshift_l(0u, MASKED ? (inb & 1u) : 1u, bin << 4);
     if (MASKED) off = (off & inb) | (lane4 & ~inb);
+#ifdef IMFEAT_CHECKS_SELFTEST
+    IMFEAT_CHECK(off < 64u);                               // control: must fire (shows that the checks are live)
+#endif
+    IMFEAT_CHECK(off < (uint32_t)(kK2cWords * 4) && (off & 3u) == 0u);
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_addr(S.hist) + off), "r"(inc) : "memory");
 }
 

@@ -182,6 +182,7 @@ __device__ __forceinline__ void k2_percentiles(const K2Smem& S, const K2Group& G
             const int sl = __shfl_sync(0xffffffffu, 8 * lane + t1, src);
             const int base = __shfl_sync(0xffffffffu, below, src);       // pixels in the slices below
             if (sl != sl_prev) {                           // level 2: lane l holds the values 8l .. 8l+7 of the slice
+                IMFEAT_CHECK(sl >= 0 && sl < 256 && own != 0u);
                 const uint4 q = reinterpret_cast<const uint4*>(S.hist)[sl * 32 + lane];
                 d[0] = (int)(q.x & 0xffffu); d[1] = (int)(q.x >> 16); d[2] = (int)(q.y & 0xffffu); d[3] = (int)(q.y >> 16);
                 d[4] = (int)(q.z & 0xffffu); d[5] = (int)(q.z >> 16); d[6] = (int)(q.w & 0xffffu); d[7] = (int)(q.w >> 16);
@@ -196,6 +197,7 @@ __device__ __forceinline__ void k2_percentiles(const K2Smem& S, const K2Group& G
             }
             const int r1 = base + in2, r0 = r1 - tl;
             const uint32_t own2 = __ballot_sync(0xffffffffu, rk[j] >= r0 && rk[j] < r1);
+            IMFEAT_CHECK(own2 != 0u && (own2 & (own2 - 1u)) == 0u);          // exactly one lane holds the rank
             const int t2 = k2_locate8(d, rk[j] - r0);
             val[j] = __shfl_sync(0xffffffffu, sl * 256 + 8 * lane + t2, __ffs(own2) - 1);
         }

@@ -91,6 +91,9 @@ struct alignas(16) K3Smem {                     // behind the table (64 or 32 KB
 struct K3Group {                               // where the quantised tile and its mask bits live
     uint32_t* q8;                              // quantised pixels (bytes) + slack for unaligned reads
     uint32_t* mbits;                           // one bit per pixel: inside the mask (masked variant)
+#ifdef IMFEAT_CHECKS
+    int q8_words, mb_words;                    // their sizes, for the bounds checks
+#endif
 };
 __host__ __device__ inline size_t k3_smem_bytes(K3Cap max_pixels, bool masked, int table_kb) {
     // two record buffers: the next tile lands while this one is worked off
@@ -225,10 +228,12 @@ __device__ __forceinline__ bool k3_item(const K3Group& Gp, const K3Geom& G, int 
 #ifdef IMFEAT_EXP_NOMASKBITS
         pm &= Gp.mbits[mi >> 5] | 0xffu;
 #else
+        IMFEAT_CHECK(mi >= 0 && mi + G.pad[2] >= 0 && (mi >> 5) + 1 < Gp.mb_words && ((mi + G.pad[2]) >> 5) + 1 < Gp.mb_words);
         pm &= k3_bits(Gp.mbits, mi) & k3_bits(Gp.mbits, mi + G.pad[2]);
 #endif
         if (pm == 0u) return false;
     }
+    IMFEAT_CHECK(oi >= 0 && oj >= 0 && (oi >> 2) + NG < Gp.q8_words && (oj >> 2) + NG < Gp.q8_words);
     const uint32_t* bi = Gp.q8 + (oi >> 2);
     const uint32_t* bj = Gp.q8 + (oj >> 2);
     const uint32_t si = (uint32_t)(oi & 3) << 3, sj = (uint32_t)(oj & 3) << 3;
@@ -357,6 +362,8 @@ __device__ __forceinline__ void k3_build4(uint32_t hist_addr, uint32_t I4, uint3
     k3_pack4<MODE>(I4, J4, V1, X, R, H, E);
     keep[0] = k3_addr<0, SH>(hist_addr, X, R); keep[1] = k3_addr<1, SH>(hist_addr, X, R);
     keep[2] = k3_addr<2, SH>(hist_addr, X, R); keep[3] = k3_addr<3, SH>(hist_addr, X, R);
+    IMFEAT_CHECK(keep[0] - hist_addr < (uint32_t)K3Mode<MODE>::kTableKB * 1024u && keep[1] - hist_addr < (uint32_t)K3Mode<MODE>::kTableKB * 1024u &&
+                 keep[2] - hist_addr < (uint32_t)K3Mode<MODE>::kTableKB * 1024u && keep[3] - hist_addr < (uint32_t)K3Mode<MODE>::kTableKB * 1024u);
     k3_red(keep[0], k3_inc<0>(H, E));
     k3_red(keep[1], k3_inc<1>(H, E));
     k3_red(keep[2], k3_inc<2>(H, E));
@@ -470,6 +477,9 @@ k3a_front_kernel(const __grid_constant__ Params P, K3Cap max_pixels, uint32_t ti
     K3Group Gp;
     Gp.mbits = reinterpret_cast<uint32_t*>(mine + sizeof(K3Hdr));
     Gp.q8 = Gp.mbits + k3_mb_words(max_pixels.mb, MASKED);
+#ifdef IMFEAT_CHECKS
+    Gp.q8_words = k3_q8_words(max_pixels.q8); Gp.mb_words = k3_mb_words(max_pixels.mb, MASKED);
+#endif
     uint32_t* recs = reinterpret_cast<uint32_t*>(mine + rec_bytes);      // [n_angles][kK3Rec]
     uint32_t* const rec_len = reinterpret_cast<uint32_t*>(scratch + (size_t)n_local_host * rec_bytes);
     auto tile_of = [&](long long tl) -> long long {          // global tile index of local tile tl
@@ -585,7 +595,9 @@ k3a_front_kernel(const __grid_constant__ Params P, K3Cap max_pixels, uint32_t ti
         if (tier.wl_out && q8_used > (uint32_t)max_pixels.q8) {
             // the rows of this mask's bounding box do not fit this tier: leave the tile to the next one
             if (lane == 0) {
-                tier.wl_out[atomicAdd(tier.n_out, 1u)] = (uint32_t)tile_id;
+                const uint32_t wpos = atomicAdd(tier.n_out, 1u);
+                IMFEAT_CHECK(wpos < n_local_host);
+                tier.wl_out[wpos] = (uint32_t)tile_id;
                 rec_len[tl] = kK3Skip;
             }
             __syncwarp();
@@ -606,9 +618,11 @@ k3a_front_kernel(const __grid_constant__ Params P, K3Cap max_pixels, uint32_t ti
             }
             const uint32_t lo = __byte_perm(q[0], q[1], 0x5410), hi = __byte_perm(q[2], q[3], 0x5410);
             if (pitch == tw) {
+                IMFEAT_CHECK(2 * idx - (qbias >> 2) >= 0 && 2 * idx - (qbias >> 2) + 1 < k3_q8_words(max_pixels.q8));
                 *reinterpret_cast<uint2*>(Gp.q8 + 2 * idx - (qbias >> 2)) = make_uint2(lo, hi);
             } else {                                       // the chunk lies inside one row (tw % 8 == 0)
                 const int ra = (int)(((float)idx + 0.5f) * rcpr);
+                IMFEAT_CHECK(ra >= brmin && (((ra - brmin) * pitch) >> 2) + 2 * (idx - ra * cpr) + 1 < k3_q8_words(max_pixels.q8));
                 uint32_t* dst = Gp.q8 + (((ra - brmin) * pitch) >> 2) + 2 * (idx - ra * cpr);
                 dst[0] = lo; dst[1] = hi;
             }
@@ -633,6 +647,7 @@ k3a_front_kernel(const __grid_constant__ Params P, K3Cap max_pixels, uint32_t ti
         // geometry of the directions: lane a works out direction a
         if (lane < P.n_angles) H.geom[lane] = k3_geom<MASKED, NG>(tw, P.dr[lane], P.dc[lane], brmin, brmax, bcmin, bcmax, qbias);
         const uint32_t len = ((uint32_t)sizeof(K3Hdr) + 4u * (uint32_t)k3_mb_words(max_pixels.mb, MASKED) + q8_used + 15u) & ~15u;
+        IMFEAT_CHECK(len <= (uint32_t)rec_bytes && (int)q8_used <= max_pixels.q8 + 32);
         if (lane == 0) {
             H.rec = reinterpret_cast<uint32_t*>(T.out_row + P.col_glcm + T.slot * P.n_angles * kNGlcm);
             H.tile = (uint32_t)tile_id; H.len = len;
@@ -729,6 +744,7 @@ k3_glcm_kernel(const __grid_constant__ Params P, K3Cap max_pixels, uint32_t n_lo
     // buffers: the record of tile j + 1 travels while tile j is worked off
     auto fetch = [&](uint32_t tl, uint32_t b, uint32_t len) { // thread 0
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // earlier generic reads of the buffer vs the async write
+        IMFEAT_CHECK(len >= kK3Skip && len <= rec_bytes && (len & 15u) == 0u && tl < n_local_host);
         mbar_expect_tx(bar0 + 8 * b, len);
         bulk_g2s(rec_addr0 + b * rec_bytes, scratch + (size_t)tl * rec_bytes, len, bar0 + 8 * b);
     };
@@ -751,6 +767,9 @@ k3_glcm_kernel(const __grid_constant__ Params P, K3Cap max_pixels, uint32_t n_lo
         K3Group Gp;
         Gp.mbits = reinterpret_cast<uint32_t*>(recbuf0 + b * rec_bytes + sizeof(K3Hdr));
         Gp.q8 = Gp.mbits + k3_mb_words(max_pixels.mb, MASKED);
+#ifdef IMFEAT_CHECKS
+        Gp.q8_words = k3_q8_words(max_pixels.q8); Gp.mb_words = k3_mb_words(max_pixels.mb, MASKED);
+#endif
         mbar_wait(bar0 + 8 * b, (j >> 1) & 1u);            // ---- record landed ----
         if (S.tlen[j & 3u] == kK3Skip) {                   // a tile left to the second tier: nothing to do here
             if (tid == 0) { S.tq[(j + 2) & 3u] = t_draw; S.tlen[(j + 2) & 3u] = len_draw; }

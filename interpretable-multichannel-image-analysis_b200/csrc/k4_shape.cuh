@@ -520,6 +520,7 @@ __global__ void __launch_bounds__(32, IMFEAT_K4W_WARPS) k4w_shape_kernel(const _
                 {
                     const uint32_t bb = c < 0 ? bits8 >> (-c) : bits8;
                     const int pos = max(c, 0), sh = pos & 31;
+                    IMFEAT_CHECK(r >= 0 && r < h && r * Pw + (pos >> 5) < kK4wWords && pos + 7 - (c < 0 ? -c : 0) < 32 * Pw + 8);
                     uint32_t* wp = mrow + r * Pw + (pos >> 5);
                     atomicOr(wp, bb << sh);
                     if (sh > 24 && (bb >> (32 - sh)) != 0u) atomicOr(wp + 1, bb >> (32 - sh));
