@@ -22,7 +22,10 @@ namespace imfeat {
 constexpr int kK12Clc = 64;     // counts below this take c * log2(c) from shared memory
 struct K12Smem {
     K2cSmem h;                  // 4,096-bin histogram (16-bit counters) + percentile scratch of this warp
-    K1Pending pending[32];      // finished tiles whose moment epilogues run 32 at a time
+#ifndef IMFEAT_K12_PARK
+#define IMFEAT_K12_PARK 16               // 16 instead of 32: 1.4 KB less shared memory per warp, 21 instead of 19 warps per SM (K12 0.581 -> 0.573 ms)
+#endif
+    K1Pending pending[IMFEAT_K12_PARK];      // finished tiles whose moment epilogues run side by side
     double clc[kK12Clc];        // c * log2(c), c < kK12Clc (0 for c = 0, 1)
 };
 
@@ -391,7 +394,7 @@ __global__ void __launch_bounds__(32, IMFEAT_K12_WARPS) k12_basic_kernel(const _
                 worklist[atomicAdd(worklist_count, 1u)] = (uint32_t)t;
             }
         }
-        if (n_pending == 32) { k1_flush(pending, 32, lane); n_pending = 0; }
+        if (n_pending == IMFEAT_K12_PARK) { k1_flush(pending, IMFEAT_K12_PARK, lane); n_pending = 0; }
     }
     k1_flush(pending, n_pending, lane);
 }
