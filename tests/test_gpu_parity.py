@@ -685,3 +685,52 @@ def test_round2_paths_edge_cases(torch_mod):
                     want[0, col] = np.percentile(sel, q) if sel.size else np.nan
             compare_tables(got[i:i + 1], want, cols, label="r2 edge %d %s mask=%s" % (i, o.shape[:2], use_mask),
                            images=[o], masks=[m] if use_mask else None)
+
+
+def test_k3_tiers_over_several_chunks_and_large_full_range_tiles(torch_mod):
+    """Two capacity tiers of K3 (strides above 8,192 pixels with masks) when the batch is worked off in several
+    front / bins rounds (IMFEAT_K3_CHUNK, read when the context is created): sparse masks stay in the first tier,
+    full and half-plane masks are listed for the second, in every round.  The same batch has full-16-bit planes of
+    128x128 pixels, more than one pass of K2's thread groups over a tile."""
+    import os
+    rng = np.random.default_rng(99)
+    C, n = 2, 23
+    objs, masks = [], []
+    for k in range(n):
+        h, w = (128, 128) if k % 5 == 0 else (int(rng.integers(40, 129)), int(rng.integers(40, 129)))
+        o = np.empty((h, w, C), np.uint16)
+        o[:, :, 0] = rng.integers(0, 65536, (h, w))                      # full range: K12's window fails, K2 takes it
+        o[:, :, 1] = rng.integers(200, 2500, (h, w))
+        m = np.zeros((h, w, C), np.uint8)
+        if k % 3 == 0:
+            m[:] = 1                                                    # whole plane: second tier
+        elif k % 3 == 1:
+            r0, c0 = int(rng.integers(0, h - 12)), int(rng.integers(0, w - 12))
+            m[r0:r0 + 12, c0:c0 + 9, :] = 1                             # sparse: first tier
+        else:
+            m[h // 3:, :, 0] = 1                                        # two thirds of the rows: second tier
+            m[:, :, 1] = rng.random((h, w)) < 0.02                      # scattered pixels over all rows: second tier
+        objs.append(o)
+        masks.append(m)
+    old = os.environ.get("IMFEAT_K3_CHUNK")
+    os.environ["IMFEAT_K3_CHUNK"] = "5"                                  # 5 objects per round: 5 rounds
+    try:
+        ex = imf.FeatureExtractor(glcm=True, four_directions=True, shape=True, moments=True)
+    finally:
+        if old is None:
+            os.environ.pop("IMFEAT_K3_CHUNK", None)
+        else:
+            os.environ["IMFEAT_K3_CHUNK"] = old
+    # fixed-stride (h,w,c) slab + size table through this extractor's host entry point
+    hs, ws = max(o.shape[0] for o in objs), max(o.shape[1] for o in objs)
+    img, msk = np.zeros((n, hs, ws, C), np.uint16), np.zeros((n, hs, ws, C), np.uint8)
+    sizes = np.zeros((n, 2), np.int32)
+    for i, (o, m) in enumerate(zip(objs, masks)):
+        img[i, :o.shape[0], :o.shape[1]] = o
+        msk[i, :o.shape[0], :o.shape[1]] = m
+        sizes[i] = o.shape[:2]
+    got = ex.extract_host_hwc(img, msk, sizes=sizes)
+    cols = imf.feature_columns(C, n_angles=4, shape=True, moments=True)
+    for i, (o, m) in enumerate(zip(objs, masks)):
+        want = c_oracle.table(_planar(o[None]), _planar(m[None]), glcm=True, n_angles=4, shape=True, moments=True)
+        compare_tables(got[i:i + 1], want, cols, label="tiers %d %s" % (i, o.shape[:2]), images=[o], masks=[m])
