@@ -215,7 +215,8 @@ def side_records(torch, imf, dev, local, planes, masks, n_obj, steps, peak):
     out5 = torch.empty((n5, ex4.row_width(c5)), dtype=torch.float64, device=dev)
     ex4.enable_timing(True)
     ex4.kernel_times(reset=True)
-    ms5 = _timed(torch, lambda: ex4.extract_planar(p5, m5, z5, hs=s5, ws=s5, out=out5), 3, warmup=1)
+    # (two warm-up calls: the context hands out two K3 scratch slots in turn, and each grows on its first use here)
+    ms5 = _timed(torch, lambda: ex4.extract_planar(p5, m5, z5, hs=s5, ws=s5, out=out5), 4, warmup=2)
     k5, c5n = ex4.kernel_times(reset=True)
     px5 = float((z5[:, 0].double() * z5[:, 1].double()).sum().item()) * c5
     b5 = px5 * 3 + n5 * 8 * F_FULL * c5
@@ -230,7 +231,7 @@ def side_records(torch, imf, dev, local, planes, masks, n_obj, steps, peak):
     g.manual_seed(16)
     p16 = torch.randint(0, 65536, tuple(planes.shape), generator=g, device=dev, dtype=torch.int32).to(torch.uint16)
     out16 = torch.empty((n_obj, ex4.row_width(C)), dtype=torch.float64, device=dev)
-    ms16 = _timed(torch, lambda: ex4.extract_planar(p16, masks, hs=HS, ws=WS, out=out16), 3, warmup=1)
+    ms16 = _timed(torch, lambda: ex4.extract_planar(p16, masks, hs=HS, ws=WS, out=out16), 4, warmup=2)
     k16, c16 = ex4.kernel_times(reset=True)
     ex4.enable_timing(False)
     rec["full_16bit_range"] = {
