@@ -390,6 +390,24 @@ def run_b200(args):
             traffic, tsrc = tj["step_total_bytes"], "profiles/r2_traffic.json (ncu dram__bytes_read+write, summed over the kernels of one step)"
         except Exception:
             traffic = None
+    # what bounds each kernel group, from the committed ncu capture of this workload (profiles/r2_traffic.json:
+    # shared-memory wavefronts per SM clock; 1.0 is the pipe's peak) -- the HBM fraction alone would not say
+    try:
+        tk = json.load(open(tpath))["kernels"] if (world == 1 and n_obj == 10000) else {}
+    except Exception:
+        tk = {}
+    if tk:
+        smem = lambda *keys: [round(v["shared_wavefronts_per_sm_clock"], 3) for k, v in tk.items() if any(q in k for q in keys)]
+        for d in per_kernel:
+            if d["kernel"].startswith("k3_"):
+                d["bound"] = "shared-memory pipe"
+                d["smem_wavefronts_per_sm_clock"] = smem("k3a_front", "k3_glcm_kernel")
+            elif d["kernel"].startswith("k12"):
+                d["bound"] = "instruction issue (62 % of peak, ncu)"
+                d["smem_wavefronts_per_sm_clock"] = smem("k12_basic")
+            elif d["kernel"].startswith("k4_"):
+                d["bound"] = "instruction issue (64 % of peak, ncu)"
+                d["smem_wavefronts_per_sm_clock"] = smem("k4w_shape")
     basic_ms = sum(d["ms_per_step"] for d in per_kernel[:2] if d["kernel"].startswith(("k12", "k2_")))
     cpu = None
     if world == 1 and not args.no_cpu:
