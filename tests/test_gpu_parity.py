@@ -734,3 +734,24 @@ def test_k3_tiers_over_several_chunks_and_large_full_range_tiles(torch_mod):
     for i, (o, m) in enumerate(zip(objs, masks)):
         want = c_oracle.table(_planar(o[None]), _planar(m[None]), glcm=True, n_angles=4, shape=True, moments=True)
         compare_tables(got[i:i + 1], want, cols, label="tiers %d %s" % (i, o.shape[:2]), images=[o], masks=[m])
+
+
+def test_maximum_plane_size(torch_mod):
+    """Planes at the size limit of the C ABI (IMFEAT_MAX_PIXELS = 32,768 pixels: 128x256 and 181x181), with a
+    sparse mask (first K3 tier), a full mask (second tier) and without masks; K4 leaves its warp-per-tile path
+    above 16,384 pixels."""
+    rng = np.random.default_rng(123)
+    cols = imf.feature_columns(1, n_angles=4, shape=True, moments=True)
+    for (h, w) in ((128, 256), (181, 181)):
+        o = np.empty((2, h, w, 1), np.uint16)
+        o[0, :, :, 0] = rng.integers(50, 4000, (h, w))
+        o[1, :, :, 0] = rng.integers(0, 65536, (h, w))
+        m = np.zeros((2, h, w, 1), np.uint8)
+        m[0, 40:70, 90:140, 0] = 1
+        m[1] = 1
+        got = imf.extract_features(o, m, four_directions=True, shape=True, moments=True)
+        want = c_oracle.table(_planar(o), _planar(m), glcm=True, n_angles=4, shape=True, moments=True)
+        compare_tables(got, want, cols, label="max size masked %dx%d" % (h, w), images=list(o), masks=list(m))
+        got = imf.extract_features(o, four_directions=True, shape=True, moments=True)
+        want = c_oracle.table(_planar(o), glcm=True, n_angles=4, shape=True, moments=True)
+        compare_tables(got, want, cols, label="max size %dx%d" % (h, w), images=list(o))
