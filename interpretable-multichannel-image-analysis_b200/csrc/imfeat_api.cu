@@ -13,6 +13,7 @@
 #include "k1_moments.cuh"
 #include "k2_order_entropy.cuh"
 #include "k12_basic.cuh"
+#include "k2b_bytes.cuh"
 #include "k3_glcm.cuh"
 #include "k3_ring.cuh"
 #include "k4_shape.cuh"
@@ -63,7 +64,8 @@ struct imfeat_ctx {
     cudaEvent_t t_side[kTimingSlots][2];   // K4 on the side stream (overlap mode): its own start / end
     // overlap mode: K4w runs on a side stream next to K3 (its few resident warps fill the issue slots the
     // shared-memory-bound GLCM kernels leave free)
-    int env_overlap, env_k4_fill, env_k3_tiers;
+    int env_overlap, env_k4_fill, env_k3_tiers, env_k2_bytes;
+    int k2b_bps[2];
     cudaStream_t side[4];
     cudaEvent_t fork_ev[8], join_ev[8];
     unsigned int side_head;
@@ -168,6 +170,7 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
         ctx->env_overlap = flag("IMFEAT_OVERLAP", 0);       // 1: K4w on a side stream next to K3, 2: next to K12 as well (measured: no gain); 0: one stream
         ctx->env_k4_fill = flag("IMFEAT_K4_FILL", 4);       // resident K4w warps per SM while it runs next to K3
         if (ctx->env_k4_fill < 1) ctx->env_k4_fill = 1;
+        ctx->env_k2_bytes = flag("IMFEAT_K2_BYTES", 1);      // 0: full-range tiles straight to K2's single 16-bit table
         ctx->env_k3_tiers = flag("IMFEAT_K3_TIERS", 1);     // 0: K3 with room for a whole tile only (no first tier for large strides)
     }
     ctx->sm_count = prop.multiProcessorCount;
@@ -195,6 +198,10 @@ int imfeat_create(int device, imfeat_ctx** out_ctx) {
     free(tab);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_order_entropy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_order_entropy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k2b_order_entropy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2bSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k2b_order_entropy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2bSmem));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2b_bps[0], k2b_order_entropy_kernel<false>, kK2bThreads, sizeof(K2bSmem));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->k2b_bps[1], k2b_order_entropy_kernel<true>, kK2bThreads, sizeof(K2bSmem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, false, 128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_glcm_kernel<false, true, 128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -604,8 +611,20 @@ static int launch_all(imfeat_ctx* ctx, const Params& P_in, const imfeat_opts* o,
             if (masked) k12_basic_kernel<true><<<g, 32, 0, st>>>(P, wl + 1, wl);
             else k12_basic_kernel<false><<<g, 32, 0, st>>>(P, wl + 1, wl);
             IMFEAT_MARK(0)
-            if (masked) k2_order_entropy_kernel<true><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, wl + 1, wl);
-            else k2_order_entropy_kernel<false><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, wl + 1, wl);
+            // the tiles K12 left over: private byte-counter tables first (three CTAs per SM, no hand-over); what
+            // wraps a byte counter goes on to K2's 16-bit table through a second list
+            uint32_t* wl_k2 = wl;
+            if (ctx->env_k2_bytes && ctx->k2b_bps[masked] > 0) {
+                wl_k2 = ctx->d_worklist + (size_t)(ctx->wl_head++ % kWlSlots) * ctx->worklist_cap;
+                CU(cudaMemsetAsync(wl_k2, 0, sizeof(uint32_t), st));
+                const long long resb = sm * ctx->k2b_bps[masked];
+                const int gb = (int)(P.n_tiles < resb ? P.n_tiles : resb);
+                if (masked) k2b_order_entropy_kernel<true><<<gb, kK2bThreads, sizeof(K2bSmem), st>>>(P, wl + 1, wl, wl_k2 + 1, wl_k2, P.sched + 1);
+                else k2b_order_entropy_kernel<false><<<gb, kK2bThreads, sizeof(K2bSmem), st>>>(P, wl + 1, wl, wl_k2 + 1, wl_k2, P.sched + 1);
+                ctx->launches += 1;
+            }
+            if (masked) k2_order_entropy_kernel<true><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, wl_k2 + 1, wl_k2);
+            else k2_order_entropy_kernel<false><<<g2, 1024, sizeof(K2Smem), st>>>(P, ng2, wl_k2 + 1, wl_k2);
             ctx->launches += 2;
             IMFEAT_MARK(1)
         } else {
