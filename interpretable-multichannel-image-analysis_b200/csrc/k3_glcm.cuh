@@ -225,12 +225,8 @@ __device__ __forceinline__ bool k3_item(const K3Group& Gp, const K3Geom& G, int 
     }
     if (MASKED) {
         const int mi = (G.r0 + r) * G.pad[1] + c;
-#ifdef IMFEAT_EXP_NOMASKBITS
-        pm &= Gp.mbits[mi >> 5] | 0xffu;
-#else
         IMFEAT_CHECK(mi >= 0 && mi + G.pad[2] >= 0 && (mi >> 5) + 1 < Gp.mb_words && ((mi + G.pad[2]) >> 5) + 1 < Gp.mb_words);
         pm &= k3_bits(Gp.mbits, mi) & k3_bits(Gp.mbits, mi + G.pad[2]);
-#endif
         if (pm == 0u) return false;
     }
     IMFEAT_CHECK(oi >= 0 && oj >= 0 && (oi >> 2) + NG < Gp.q8_words && (oj >> 2) + NG < Gp.q8_words);
@@ -261,7 +257,7 @@ __device__ __forceinline__ void k3_sums(const double* homtab, uint32_t I4, uint3
     A.sij = __dp4a(I4, J4, A.sij);
     A.sd += __vsadu4(I4, J4);
     const uint32_t D4 = __vabsdiffu4(I4, J4);
-#ifdef IMFEAT_EXP_NOHOM
+#ifdef IMFEAT_EXP_NOHOM                                    // measurement only (wrong results): what the look-ups cost at most
     A.hom0 += (double)D4; return;
 #endif
     A.hom0 += homtab[D4 & 0xffu];                  // two chains: a DADD waits several cycles for the one before it
